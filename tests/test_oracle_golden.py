@@ -1,0 +1,101 @@
+"""Pin the oracle port (oracle/af_oracle.py) against golden vectors minted from the unmodified
+reference (oracle/make_golden.py).  Forward results must be bitwise equal on the same torch
+build; gradients within 1e-5 of the gradient scale."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import af_oracle as O
+from oracle import cases
+
+
+def _close(a, b, rel=1e-5):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    scale = max(np.abs(b).max(), 1e-30)
+    return np.abs(a - b).max() <= rel * scale
+
+
+def test_r6(golden_dir):
+    g = np.load(os.path.join(golden_dir, "r6.npz"))
+    o = torch.from_numpy(g["ortho"]).requires_grad_(True)
+    m = O.r6_to_matrix(o)
+    assert np.array_equal(m.detach().numpy(), g["mat"])
+    (m * cases.pattern(m.shape, 1.0)).sum().backward()
+    assert _close(o.grad.numpy(), g["d_ortho"])
+
+
+@pytest.mark.parametrize("tag,kw", [
+    ("slice", dict(target_fov_mm=torch.tensor([30.0, 20.0, 1.5]), target_fov_vox=torch.tensor([16, 12, 1]))),
+    ("vol3d", dict(target_fov_mm=torch.tensor([28.0, 30.0, 33.0]), target_fov_vox=torch.tensor([9, 10, 11]))),
+    ("same", dict())])
+def test_slice_small(golden_dir, tag, kw):
+    g = np.load(os.path.join(golden_dir, "slice_small.npz"))
+    B, C, D, H, W = 2, 3, 20, 24, 28
+    vol = cases.randn((B, C, D, H, W), 21).requires_grad_(True)
+    lab = cases.randint(0, 6, (B, C, D, H, W), 22)
+    nii = torch.from_numpy(g["nii"]); P = torch.from_numpy(g["P"]).requires_grad_(True)
+    y, ga, na = O.nifti_grid_sample(vol, nii, is_label=False, pre_grid_sample_affine=P, **kw)
+    assert np.array_equal(y.detach().numpy(), g[f"{tag}_y"])
+    assert np.array_equal(ga.detach().numpy(), g[f"{tag}_ga"])
+    assert np.allclose(na.detach().numpy(), g[f"{tag}_nii"], rtol=1e-12, atol=1e-12)
+    ((y * cases.pattern(y.shape, 1.0)).sum() + (ga * cases.pattern(ga.shape, 2.0)).sum()).backward()
+    assert _close(vol.grad.numpy(), g[f"{tag}_dvol"])
+    assert _close(P.grad.numpy(), g[f"{tag}_dP"])
+    yl, _, _ = O.nifti_grid_sample(lab, nii, is_label=True, pre_grid_sample_affine=P.detach(), **kw)
+    assert yl.dtype == torch.int64 and np.array_equal(yl.numpy(), g[f"{tag}_ylabel"])
+
+
+def test_slice_cfg1_128(golden_dir):
+    g = np.load(os.path.join(golden_dir, "slice_cfg1_128.npz"))
+    syn = cases.synthetic
+    vol = torch.from_numpy(syn.phantom_image(syn.heart_phantom(128), seed=5))[None, None].requires_grad_(True)
+    r6 = torch.from_numpy(g["r6"]).requires_grad_(True)
+    P = torch.from_numpy(g["gpre"]) @ O.r6_to_matrix(r6)
+    y, ga, na = O.nifti_grid_sample(vol, syn.default_nifti_affine(1), target_fov_mm=torch.tensor([192.0, 192.0, 1.5]),
+                                    target_fov_vox=torch.tensor([128, 128, 1]), pre_grid_sample_affine=P)
+    assert np.array_equal(y.detach().numpy(), g["y"]) and np.array_equal(ga.detach().numpy(), g["ga"])
+    (y * cases.pattern(y.shape, 1.0)).sum().backward()
+    assert _close(r6.grad.numpy(), g["d_r6"])
+    dv = vol.grad[0, 0]
+    assert _close(dv.sum(0).numpy(), g["dvol_sum_d"]) and _close(dv.sum(2).numpy(), g["dvol_sum_w"])
+
+
+@pytest.mark.parametrize("tag,zc", [("atm_s32", 0.0), ("atm_s32_zoom", 0.3)])
+def test_atm_s32(golden_dir, tag, zc):
+    g = np.load(os.path.join(golden_dir, tag + ".npz"))
+    case = cases.atm_case(32, 2, 3, seed=41, zoom_clip=zc)
+    for v in range(3):
+        assert np.array_equal(case["gpre"][v].numpy(), g["gpre"][v])
+        params = case["params"][v].clone().requires_grad_(True)
+        soft = case["soft"].clone().requires_grad_(True)
+        theta = O.view_theta(params, torch.tensor([[1e-2, 0, 0, 0, 1e-2, 0]]), torch.zeros(3), torch.ones(1, 1),
+                             case["offset_clip"], zc, 32)
+        assert np.array_equal(theta.detach().numpy(), g[f"theta{v}"])
+        ys, yl, yi, ga, na = O.atm_tail_forward(soft, case["label"], case["image"], case["nii"], case["gpre"][v], theta,
+                                                case["slice_fov_mm"], case["slice_fov_vox"])
+        assert np.array_equal(ys.detach().numpy(), g[f"ys{v}"])
+        assert np.array_equal(yl.numpy().astype(np.uint8), g[f"yl{v}"])
+        assert np.array_equal(yi.numpy(), g[f"yi{v}"])
+        assert np.array_equal(ga.detach().numpy(), g[f"ga{v}"])
+        ((ys * cases.pattern(ys.shape, 1.0 + v)).sum() + (ga * cases.pattern(ga.shape, 2.0 + v)).sum()).backward()
+        assert _close(params.grad.numpy(), g[f"dparams{v}"])
+        assert _close(soft.grad.sum(-1).numpy(), g[f"dsoft_sum_w{v}"])
+
+
+@pytest.mark.parametrize("tag,shape", [("embed_s16", (16, 3, 2, 2)), ("embed_s8", (8, 4, 3, 2)), ("embed_s32", (32, 4, 6, 1))])
+def test_embed(golden_dir, tag, shape):
+    S, c, V, B = shape
+    g = np.load(os.path.join(golden_dir, tag + ".npz"))
+    case = cases.embed_case(S, c, V, B, seed=51 + S)
+    x = case["x"].clone().requires_grad_(True)
+    gas = [a.clone().requires_grad_(True) for a in case["affines"]]
+    assert np.array_equal(np.stack([a.detach().numpy() for a in gas]), g["affines"])
+    out = O.skip_connector(x, gas, V)
+    assert np.array_equal(out.detach().numpy(), g["out"])
+    (out * cases.pattern(out.shape, 1.0)).sum().backward()
+    assert _close(x.grad.numpy(), g["dx"])
+    assert _close(np.stack([a.grad.numpy() for a in gas]), g["d_affines"], rel=1e-4)
+    sp = O.skip_connector_sparse(x.detach(), [a.detach() for a in gas], V)
+    assert _close(sp.numpy(), g["out"], rel=1e-5)
