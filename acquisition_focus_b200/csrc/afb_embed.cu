@@ -1,0 +1,304 @@
+// afb_embed.cu - slice -> 3-D embedding of the hybrid U-Net skip connections
+// (models/hybrid_unet.py:71-94, SkipConnector.forward) forward and backward.
+//
+// The reference builds a zero S^3 volume per channel, writes the 2-D feature map onto the plane
+// W = S/2 (x_mid, :75-76), materialises a [B,S,S,S,3] grid from inverse(normalised slicing affine)
+// (:83-87) and calls grid_sample (:88-90).  Here neither x_mid nor the grid exists: for an output
+// voxel only the corners with x index == S/2 can be non-zero, so
+//     out = wx(ix) * bilinear2D_zeros(x[b,ch], row = iz, col = iy)
+// with the identical coordinate / weight arithmetic (afb_device.cuh), i.e. bitwise the same value
+// for the same inverse affine.  The forward is a pure HBM write stream (B*V*c*S^3*4 bytes):
+// one thread = 4 consecutive w (one 16-byte streaming store per channel), coordinates computed once
+// and reused across the c channels of the view.
+#include "afb_device.cuh"
+
+namespace afb {
+
+constexpr int ETHREADS = 256;
+
+struct EmbedView {            // per (b, v), shared memory
+    float t[12];              // inverse(normalised affine)[:3,:] fp32 = affine_grid theta
+    double ga[16], n[3], Ainv[16];
+};
+
+// ga -> A = ga diag(1/|col|) -> A^-1 (affine: last row 0 0 0 1), hybrid_unet.py:83-86. One thread.
+__device__ inline void embed_prologue(const float* __restrict__ ga_in, EmbedView& ev) {
+    for (int i = 0; i < 16; ++i) ev.ga[i] = (double)ga_in[i];
+    float nf[3];
+    for (int j = 0; j < 3; ++j) {
+        // fp32 column norm and reciprocal like get_zooms / 1/get_zooms on the fp32 affine
+        float a0 = ga_in[0 * 4 + j], a1 = ga_in[1 * 4 + j], a2 = ga_in[2 * 4 + j];
+        nf[j] = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1)), __fmul_rn(a2, a2)));
+        ev.n[j] = (double)nf[j];
+    }
+    double A[9], t[3];
+    for (int r = 0; r < 3; ++r) {
+        for (int j = 0; j < 3; ++j) A[r * 3 + j] = (double)__fmul_rn(ga_in[r * 4 + j], __fdiv_rn(1.0f, nf[j]));
+        t[r] = (double)ga_in[r * 4 + 3];
+    }
+    const double c00 = A[4] * A[8] - A[5] * A[7], c01 = A[5] * A[6] - A[3] * A[8], c02 = A[3] * A[7] - A[4] * A[6];
+    const double det = A[0] * c00 + A[1] * c01 + A[2] * c02;
+    const double id = 1.0 / det;
+    double inv[9];
+    inv[0] = c00 * id; inv[1] = (A[2] * A[7] - A[1] * A[8]) * id; inv[2] = (A[1] * A[5] - A[2] * A[4]) * id;
+    inv[3] = c01 * id; inv[4] = (A[0] * A[8] - A[2] * A[6]) * id; inv[5] = (A[2] * A[3] - A[0] * A[5]) * id;
+    inv[6] = c02 * id; inv[7] = (A[1] * A[6] - A[0] * A[7]) * id; inv[8] = (A[0] * A[4] - A[1] * A[3]) * id;
+    for (int r = 0; r < 3; ++r) {
+        for (int j = 0; j < 3; ++j) ev.Ainv[r * 4 + j] = inv[r * 3 + j];
+        ev.Ainv[r * 4 + 3] = -(inv[r * 3 + 0] * t[0] + inv[r * 3 + 1] * t[1] + inv[r * 3 + 2] * t[2]);
+    }
+    ev.Ainv[12] = 0.0; ev.Ainv[13] = 0.0; ev.Ainv[14] = 0.0; ev.Ainv[15] = 1.0;
+    for (int i = 0; i < 12; ++i) ev.t[i] = (float)ev.Ainv[i];
+}
+
+struct Tap {                  // the (up to) 4 contributing samples of one output voxel
+    float w[4];               // (wx*wy)*wz in ATen order (dy,dz) = (0,0),(1,0),(0,1),(1,1)
+    int off[4];               // row*S + col into x[b,ch]
+    unsigned inb;             // bit k: tap k inside the slice;  0 => voxel is zero
+    float sx;                 // +-1: d wx / d ix
+    float wx, wy[2], wz[2];
+};
+
+__device__ __forceinline__ Tap taps_of(const float* __restrict__ t, float bx, float by, float bz, int S) {
+    Tap tp;
+    tp.inb = 0u;
+    const float Sf = (float)S;
+    const float ix = unnormalize(grid_coord(t + 0, bx, by, bz), Sf);
+    const int x0 = __float2int_rd(ix);
+    const int mid = S >> 1;
+    if (x0 != mid && x0 + 1 != mid) return tp;
+    const float x0f = floorf(ix);
+    if (x0 == mid) { tp.wx = __fsub_rn(__fadd_rn(x0f, 1.0f), ix); tp.sx = -1.0f; }
+    else { tp.wx = __fsub_rn(ix, x0f); tp.sx = 1.0f; }
+    const float iy = unnormalize(grid_coord(t + 4, bx, by, bz), Sf);
+    const float iz = unnormalize(grid_coord(t + 8, bx, by, bz), Sf);
+    const float y0f = floorf(iy), z0f = floorf(iz);
+    const int y0 = __float2int_rd(iy), z0 = __float2int_rd(iz);
+    tp.wy[0] = __fsub_rn(__fadd_rn(y0f, 1.0f), iy); tp.wy[1] = __fsub_rn(iy, y0f);
+    tp.wz[0] = __fsub_rn(__fadd_rn(z0f, 1.0f), iz); tp.wz[1] = __fsub_rn(iz, z0f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int dy = k & 1, dz = k >> 1;
+        const int q = y0 + dy, r = z0 + dz;
+        const bool in = q >= 0 && q < S && r >= 0 && r < S;
+        tp.w[k] = __fmul_rn(__fmul_rn(tp.wx, tp.wy[dy]), tp.wz[dz]);
+        tp.off[k] = in ? r * S + q : 0;
+        tp.inb |= in ? (1u << k) : 0u;
+    }
+    return tp;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward: grid = (ceil(S^3/VEC / 256), B*V)
+// ------------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(ETHREADS)
+embed_fwd_kernel(const float* __restrict__ x, const float* __restrict__ affines, int B, int V, int c, int S,
+                 AxisConst ax, float* __restrict__ out) {
+    __shared__ EmbedView ev;
+    const int bv = blockIdx.y, b = bv / V, v = bv % V;
+    if (threadIdx.x == 0) embed_prologue(affines + ((size_t)v * B + b) * 16, ev);
+    __syncthreads();
+    const int wv = S / VEC;                                   // vectors per row
+    const long long nvec = (long long)S * S * wv;
+    const long long e = (long long)blockIdx.x * ETHREADS + threadIdx.x;
+    if (e >= nvec) return;
+    const int w0 = (int)(e % wv) * VEC;
+    const int h = (int)((e / wv) % S), d = (int)(e / ((long long)wv * S));
+    const float by = base_coord(h, ax), bz = base_coord(d, ax);
+    Tap tp[VEC];
+    unsigned any = 0u;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+        tp[k] = taps_of(ev.t, base_coord(w0 + k, ax), by, bz, S);
+        any |= tp[k].inb;
+    }
+    const size_t S2 = (size_t)S * S, S3 = S2 * S;
+    const float* __restrict__ xs = x + ((size_t)b * V + v) * c * S2;
+    float* __restrict__ o = out + ((size_t)b * V + v) * c * S3 + ((size_t)d * S + h) * S + w0;
+    if (any == 0u) {
+        if (VEC == 4) {
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int ch = 0; ch < c; ++ch) __stcs(reinterpret_cast<float4*>(o + (size_t)ch * S3), z4);
+        } else {
+            for (int ch = 0; ch < c; ++ch) __stcs(o + (size_t)ch * S3, 0.0f);
+        }
+        return;
+    }
+    for (int ch = 0; ch < c; ++ch) {
+        const float* __restrict__ xc = xs + (size_t)ch * S2;
+        float r[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if ((tp[k].inb >> q) & 1u) acc = __fadd_rn(acc, __fmul_rn(__ldg(xc + tp[k].off[q]), tp[k].w[q]));
+            r[k] = acc;
+        }
+        if (VEC == 4) __stcs(reinterpret_cast<float4*>(o + (size_t)ch * S3), make_float4(r[0], r[1], r[2], r[3]));
+        else __stcs(o + (size_t)ch * S3, r[0]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward: same scan; only slab voxels read grad_out; dX via RED, d(theta) block-reduced,
+// last CTA of a (b,v) chains d(theta) -> d(slicing affine) through inverse and normalisation.
+// ------------------------------------------------------------------------------------------------
+__device__ inline void embed_chain(const EmbedView& ev, const double* __restrict__ dT /*12*/, float* __restrict__ d_ga /*16*/) {
+    // d(Ainv) = [dT; 0] ; dA = -Ainv^T d(Ainv) Ainv^T
+    double G[16], M[16], dA[16];
+    for (int i = 0; i < 12; ++i) G[i] = dT[i];
+    for (int i = 12; i < 16; ++i) G[i] = 0.0;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            double acc = 0.0;
+            for (int k = 0; k < 4; ++k) acc += ev.Ainv[k * 4 + i] * G[k * 4 + j];
+            M[i * 4 + j] = acc;
+        }
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            double acc = 0.0;
+            for (int k = 0; k < 4; ++k) acc += M[i * 4 + k] * ev.Ainv[j * 4 + k];
+            dA[i * 4 + j] = -acc;
+        }
+    // A[:, j] = ga[:, j] / n_j  (j < 3), n_j = |ga[:3, j]|
+    for (int j = 0; j < 3; ++j) {
+        double dot = 0.0;
+        for (int r = 0; r < 4; ++r) dot += dA[r * 4 + j] * ev.ga[r * 4 + j];
+        const double n = ev.n[j];
+        for (int r = 0; r < 4; ++r) {
+            double g = dA[r * 4 + j] / n;
+            if (r < 3) g -= ev.ga[r * 4 + j] * dot / (n * n * n);
+            d_ga[r * 4 + j] = (float)g;
+        }
+    }
+    for (int r = 0; r < 4; ++r) d_ga[r * 4 + 3] = (float)dA[r * 4 + 3];
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(ETHREADS)
+embed_bwd_kernel(const float* __restrict__ go, const float* __restrict__ x, const float* __restrict__ affines,
+                 int B, int V, int c, int S, AxisConst ax, float* __restrict__ d_x, float* __restrict__ d_aff,
+                 double* __restrict__ ws_acc, unsigned* __restrict__ ws_counter) {
+    __shared__ EmbedView ev;
+    __shared__ float red[ETHREADS / 32][12];
+    __shared__ double dT[12];
+    __shared__ bool is_last;
+    const int bv = blockIdx.y, b = bv / V, v = bv % V;
+    if (threadIdx.x == 0) embed_prologue(affines + ((size_t)v * B + b) * 16, ev);
+    __syncthreads();
+    float part[12];
+#pragma unroll
+    for (int q = 0; q < 12; ++q) part[q] = 0.0f;
+    const int wv = S / VEC;
+    const long long nvec = (long long)S * S * wv;
+    const long long e = (long long)blockIdx.x * ETHREADS + threadIdx.x;
+    if (e < nvec) {
+        const int w0 = (int)(e % wv) * VEC;
+        const int h = (int)((e / wv) % S), d = (int)(e / ((long long)wv * S));
+        const float by = base_coord(h, ax), bz = base_coord(d, ax);
+        const size_t S2 = (size_t)S * S, S3 = S2 * S;
+        const float* __restrict__ xs = x + ((size_t)b * V + v) * c * S2;
+        float* __restrict__ dxs = d_x ? d_x + ((size_t)b * V + v) * c * S2 : nullptr;
+        const float* __restrict__ g = go + ((size_t)b * V + v) * c * S3 + ((size_t)d * S + h) * S + w0;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            const float bx = base_coord(w0 + k, ax);
+            const Tap tp = taps_of(ev.t, bx, by, bz, S);
+            if (tp.inb == 0u) continue;
+            float dot[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int ch = 0; ch < c; ++ch) {
+                const float gv = __ldg(g + (size_t)ch * S3 + k);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if ((tp.inb >> q) & 1u) {
+                        if (d_aff) dot[q] = fmaf(__ldg(xs + (size_t)ch * S2 + tp.off[q]), gv, dot[q]);
+                        if (dxs) atomicAdd(dxs + (size_t)ch * S2 + tp.off[q], tp.w[q] * gv);
+                    }
+                }
+            }
+            if (d_aff) {
+                float gix = 0.f, giy = 0.f, giz = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int dy = q & 1, dz = q >> 1;
+                    const float dq = ((tp.inb >> q) & 1u) ? dot[q] : 0.f;
+                    gix += tp.sx * dq * tp.wy[dy] * tp.wz[dz];
+                    giy += (dy ? dq : -dq) * tp.wx * tp.wz[dz];
+                    giz += (dz ? dq : -dq) * tp.wx * tp.wy[dy];
+                }
+                const float hs = 0.5f * (float)S;
+                const float ggx = gix * hs, ggy = giy * hs, ggz = giz * hs;
+                part[0] += ggx * bx; part[1] += ggx * by; part[2] += ggx * bz; part[3] += ggx;
+                part[4] += ggy * bx; part[5] += ggy * by; part[6] += ggy * bz; part[7] += ggy;
+                part[8] += ggz * bx; part[9] += ggz * by; part[10] += ggz * bz; part[11] += ggz;
+            }
+        }
+    }
+    if (!d_aff) return;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int q = 0; q < 12; ++q) {
+        const float r = warp_sum(part[q]);
+        if (lane == 0) red[w][q] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        double t = 0.0;
+#pragma unroll
+        for (int ww = 0; ww < ETHREADS / 32; ++ww) t += (double)red[ww][threadIdx.x];
+        if (t != 0.0) atomicAdd(ws_acc + (size_t)bv * 16 + threadIdx.x, t);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(ws_counter + bv, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x < 12) {
+        dT[threadIdx.x] = __ldcg(ws_acc + (size_t)bv * 16 + threadIdx.x);
+        ws_acc[(size_t)bv * 16 + threadIdx.x] = 0.0;
+    }
+    if (threadIdx.x == 0) ws_counter[bv] = 0u;
+    __syncthreads();
+    if (threadIdx.x == 0) embed_chain(ev, dT, d_aff + ((size_t)v * B + b) * 16);
+}
+
+}  // namespace afb
+
+using namespace afb;
+
+extern "C" int afb_embed_fwd(const float* x, const float* affines, int B, int V, int c, int S, float* out, void* stream) {
+    if (!x || !affines || !out) return AFB_EINVAL;
+    if (B <= 0 || V <= 0 || c <= 0 || S <= 0 || (long long)B * V > 65535) return AFB_ESHAPE;
+    const AxisConst ax = make_axis(S);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = (S % 4 == 0) && (((uintptr_t)out & 15u) == 0);
+    const long long nvec = (long long)S * S * (vec ? S / 4 : S);
+    dim3 grid((unsigned)((nvec + ETHREADS - 1) / ETHREADS), B * V);
+    if (vec) embed_fwd_kernel<4><<<grid, ETHREADS, 0, st>>>(x, affines, B, V, c, S, ax, out);
+    else embed_fwd_kernel<1><<<grid, ETHREADS, 0, st>>>(x, affines, B, V, c, S, ax, out);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int64_t afb_embed_bwd_workspace_bytes(int n_slices) {
+    return (int64_t)n_slices * (16 * sizeof(double) + 2 * sizeof(unsigned));
+}
+
+extern "C" int afb_embed_bwd(const float* grad_out, const float* x, const float* affines, int B, int V, int c, int S,
+                             float* d_x, float* d_affines, void* workspace, void* stream) {
+    if (!grad_out || !x || !affines || !workspace) return AFB_EINVAL;
+    if (!d_x && !d_affines) return AFB_EINVAL;
+    if (B <= 0 || V <= 0 || c <= 0 || S <= 0 || (long long)B * V > 65535) return AFB_ESHAPE;
+    const AxisConst ax = make_axis(S);
+    cudaStream_t st = (cudaStream_t)stream;
+    double* acc = (double*)workspace;
+    unsigned* counter = (unsigned*)(acc + (size_t)B * V * 16);
+    const bool vec = (S % 4 == 0);
+    const long long nvec = (long long)S * S * (vec ? S / 4 : S);
+    dim3 grid((unsigned)((nvec + ETHREADS - 1) / ETHREADS), B * V);
+    if (vec) embed_bwd_kernel<4><<<grid, ETHREADS, 0, st>>>(grad_out, x, affines, B, V, c, S, ax, d_x, d_affines, acc, counter);
+    else embed_bwd_kernel<1><<<grid, ETHREADS, 0, st>>>(grad_out, x, affines, B, V, c, S, ax, d_x, d_affines, acc, counter);
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,332 @@
+"""Autograd-aware Python entry points over the C ABI (libafb200.so).
+
+Three levels, all backed by the same two CUDA kernels (``afb_slice_fwd`` / ``afb_slice_bwd``):
+
+* :func:`affine_grid_sample` - ``F.affine_grid`` + ``F.grid_sample`` (5-D, zeros padding,
+  ``align_corners=False``) in one launch, never materialising the grid.
+* :func:`slice_with_pre_affine` - the body of the reference's ``nifti_grid_sample``
+  (``utils/nifti_utils.py:112-207``): fp64 affine bookkeeping fused into the sampler prologue,
+  min-shift semantics, returns ``(out, grid_affine, nii_affine)``.
+* :func:`acquire_views` - the tail of ``AffineTransformModule.forward``
+  (``models/learnable_transform.py:259-306``) for all B x V slices at once, from raw view
+  parameters (R6 | offset logits | zoom logit), gradients w.r.t. the parameters computed by the
+  analytic chain in the backward kernel's epilogue.
+
+plus :func:`r6_to_matrix` (``utils/transform_utils.py:27-58``) and :func:`embed_slices`
+(``models/hybrid_unet.py:71-94``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------
+def _is_dense(t: torch.Tensor) -> bool:
+    """True if the tensor covers a compact block of memory in some dim permutation."""
+    dims = sorted(range(t.dim()), key=lambda d: (t.stride(d), t.size(d)), reverse=True)
+    expect = 1
+    for d in reversed(dims):
+        if t.size(d) == 1:
+            continue
+        if t.stride(d) != expect:
+            return False
+        expect *= t.size(d)
+    return True
+
+
+def _zeros_like_strided(t: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
+    out = torch.empty_strided(t.shape, t.stride(), dtype=dtype, device=t.device)
+    return out.zero_()
+
+
+def volume_min(volume: torch.Tensor) -> torch.Tensor:
+    """``volume.min()`` of nifti_utils.py:200 as a device tensor ``[min, multiplicity]`` (fp32)."""
+    L.require_cuda(volume, "volume")
+    if not _is_dense(volume):
+        volume = volume.contiguous()
+    lib = L.lib()
+    with torch.cuda.device(volume.device):
+        ws = torch.empty(int(lib.afb_volume_min_workspace_bytes()), dtype=torch.uint8, device=volume.device)
+        out = torch.empty(2, dtype=torch.float32, device=volume.device)
+        L.check(lib.afb_volume_min(L.ptr(volume), L.DTYPES[volume.dtype], volume.numel(), L.ptr(out), L.ptr(ws),
+                                   L.stream_ptr(volume.device)), "afb_volume_min")
+    return out
+
+
+@dataclass
+class ViewSpec:
+    """Python mirror of ``afb_views`` (include/afb200.h)."""
+    kind: int
+    V: int = 1
+    theta: Optional[torch.Tensor] = None
+    pre: Optional[torch.Tensor] = None
+    params: Optional[torch.Tensor] = None
+    gpre: Optional[torch.Tensor] = None
+    init: Optional[torch.Tensor] = None
+    R: int = 0
+    spat: int = 1
+    offset_clip: float = 0.0
+    zoom_clip: float = 0.0
+    nii_affine: Optional[torch.Tensor] = None
+    fov_mm: Tuple[float, float, float] = (0.0, 0.0, 0.0)
+    _keep: list = field(default_factory=list, repr=False)
+
+    def struct(self) -> L.AfbViews:
+        s = L.AfbViews()
+        s.kind, s.V = self.kind, self.V
+        s.theta = None if self.theta is None else self.theta.data_ptr()
+        s.pre = None if self.pre is None else self.pre.data_ptr()
+        s.pre_is_f64 = int(self.pre is not None and self.pre.dtype == torch.float64)
+        s.params = None if self.params is None else self.params.data_ptr()
+        s.gpre = None if self.gpre is None else self.gpre.data_ptr()
+        s.init = None if self.init is None else self.init.data_ptr()
+        s.R, s.spat, s.offset_clip, s.zoom_clip = int(self.R), int(self.spat), float(self.offset_clip), float(self.zoom_clip)
+        s.nii_affine = None if self.nii_affine is None else self.nii_affine.data_ptr()
+        s.fov_mm = (C.c_double * 3)(*[float(v) for v in self.fov_mm])
+        return s
+
+    def diff_input(self) -> torch.Tensor:
+        return {L.AFFINE_GRID: self.theta, L.AFFINE_PRE: self.pre, L.AFFINE_PARAMS: self.params}[self.kind]
+
+    def with_diff_input(self, t: torch.Tensor) -> "ViewSpec":
+        kw = dict(self.__dict__)
+        kw.pop("_keep")
+        kw[{L.AFFINE_GRID: "theta", L.AFFINE_PRE: "pre", L.AFFINE_PARAMS: "params"}[self.kind]] = t
+        return ViewSpec(**kw)
+
+
+def _prep(t: Optional[torch.Tensor], dtype, device) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    return t.detach().to(device=device, dtype=dtype).contiguous()
+
+
+def _slice_forward_raw(volume, spec: ViewSpec, out_size, mode, pad_mode, pad_value, pad_dev, want_nii=True):
+    lib = L.lib()
+    B, Cc = volume.shape[:2]
+    S = B * spec.V
+    Do, Ho, Wo = (int(v) for v in out_size)
+    dev = volume.device
+    with torch.cuda.device(dev):
+        out = torch.empty((B, spec.V, Cc, Do, Ho, Wo), dtype=volume.dtype, device=dev)
+        ga = torch.empty((B, spec.V, 4, 4), dtype=torch.float32, device=dev)
+        nii = torch.empty((B, spec.V, 4, 4), dtype=torch.float64, device=dev) if (want_nii and spec.kind != L.AFFINE_GRID) else None
+        th = torch.empty((B, spec.V, 4, 4), dtype=torch.float32, device=dev) if spec.kind == L.AFFINE_PARAMS else None
+        vd, vs = L.volume_desc(volume), spec.struct()
+        L.check(lib.afb_slice_fwd(C.byref(vd), C.byref(vs), Do, Ho, Wo, mode, pad_mode, float(pad_value), L.ptr(pad_dev),
+                                  L.ptr(out), L.ptr(ga), L.ptr(nii), L.ptr(th), L.stream_ptr(dev)), "afb_slice_fwd")
+    return out, ga, nii, th
+
+
+class _SliceFn(torch.autograd.Function):
+    """out, grid_affine, nii_affine, theta = f(volume, view_input[, gpre])."""
+
+    @staticmethod
+    def forward(ctx, volume, view_input, spec: ViewSpec, out_size, mode, pad_mode, pad_value, pad_dev):
+        L.require_cuda(volume, "volume")
+        ctx.set_materialize_grads(False)
+        spec = spec.with_diff_input(view_input.detach().contiguous())
+        out, ga, nii, th = _slice_forward_raw(volume.detach(), spec, out_size, mode, pad_mode, pad_value, pad_dev)
+        ctx.spec, ctx.out_size, ctx.mode = spec, tuple(int(v) for v in out_size), mode
+        ctx.pad_mode, ctx.pad_value = pad_mode, pad_value
+        ctx.save_for_backward(volume.detach(), pad_dev if pad_dev is not None else torch.empty(0))
+        ctx.in_dtype = view_input.dtype
+        if nii is None:
+            nii = torch.empty(0, device=volume.device)
+        if th is None:
+            th = torch.empty(0, device=volume.device)
+        ctx.mark_non_differentiable(nii, th)
+        if mode == L.NEAREST or not volume.dtype.is_floating_point:
+            ctx.mark_non_differentiable(out)
+        return out, ga, nii, th
+
+    @staticmethod
+    def backward(ctx, g_out, g_ga, _g_nii, _g_th):
+        volume, pad_dev = ctx.saved_tensors
+        pad_dev = pad_dev if pad_dev.numel() else None
+        spec: ViewSpec = ctx.spec
+        lib = L.lib()
+        dev = volume.device
+        B = volume.shape[0]
+        S = B * spec.V
+        need_vol = ctx.needs_input_grad[0] and volume.dtype.is_floating_point and ctx.mode == L.BILINEAR
+        need_aff = ctx.needs_input_grad[1]
+        sample_grad = g_out is not None and ctx.mode == L.BILINEAR and volume.dtype.is_floating_point
+        with torch.cuda.device(dev):
+            d_vol = _zeros_like_strided(volume) if (need_vol and sample_grad) else None
+            d_aff = torch.zeros(spec.diff_input().shape, dtype=torch.float32, device=dev) if need_aff else None
+            if not sample_grad and g_ga is None:
+                return d_vol, d_aff, None, None, None, None, None, None
+            ws = torch.zeros(int(lib.afb_slice_bwd_workspace_bytes(S)), dtype=torch.uint8, device=dev)
+            d_pad = torch.zeros(1, dtype=torch.float32, device=dev) if (d_vol is not None and ctx.pad_mode == L.PAD_DEVICE) else None
+            go = g_out.contiguous().float() if sample_grad else None
+            gga = g_ga.contiguous().float() if g_ga is not None else None
+            vd, vs = L.volume_desc(volume), spec.struct()
+            Do, Ho, Wo = ctx.out_size
+            L.check(lib.afb_slice_bwd(C.byref(vd), C.byref(vs), Do, Ho, Wo, ctx.pad_mode, float(ctx.pad_value), L.ptr(pad_dev),
+                                      L.ptr(go), L.ptr(gga), L.ptr(d_vol), L.ptr(d_aff), None, L.ptr(d_pad), L.ptr(ws),
+                                      L.stream_ptr(dev)), "afb_slice_bwd")
+            if d_pad is not None:
+                L.check(lib.afb_min_grad(L.ptr(volume), L.DTYPES[volume.dtype], volume.numel(), L.ptr(pad_dev), L.ptr(d_pad),
+                                         L.ptr(d_vol), L.stream_ptr(dev)), "afb_min_grad")
+        if d_aff is not None and d_aff.dtype != ctx.in_dtype:
+            d_aff = d_aff.to(ctx.in_dtype)
+        return d_vol, d_aff, None, None, None, None, None, None
+
+
+def _run_slice(volume, view_input, spec, out_size, mode, pad):
+    """pad: 'zero' | 'global_min' | float | device tensor [min,count]."""
+    if not _is_dense(volume):
+        volume = volume.contiguous()
+    pad_mode, pad_value, pad_dev = L.PAD_ZERO, 0.0, None
+    if mode == L.BILINEAR:
+        if isinstance(pad, torch.Tensor):
+            pad_mode, pad_dev = L.PAD_DEVICE, pad
+        elif pad == "global_min":
+            pad_mode, pad_dev = L.PAD_DEVICE, volume_min(volume)
+        elif pad == "zero":
+            pass
+        else:
+            pad_mode, pad_value = L.PAD_VALUE, float(pad)
+    return _SliceFn.apply(volume, view_input, spec, out_size, mode, pad_mode, pad_value, pad_dev)
+
+
+# ------------------------------------------------------------------------------------------------
+# public ops
+# ------------------------------------------------------------------------------------------------
+def affine_grid_sample(volume: torch.Tensor, theta: torch.Tensor, size: Sequence[int], mode: str = "bilinear",
+                       pad="zero") -> torch.Tensor:
+    """``F.grid_sample(volume, F.affine_grid(theta, [N,C,*size], False), mode, 'zeros', False)``.
+
+    volume ``[N,C,D,H,W]``, theta ``[N,3,4]`` fp32 -> ``[N,C,*size]``; differentiable w.r.t. both."""
+    L.require_cuda(volume, "volume")
+    m = {"bilinear": L.BILINEAR, "nearest": L.NEAREST}[mode]
+    spec = ViewSpec(kind=L.AFFINE_GRID, V=1)
+    out, _, _, _ = _run_slice(volume, theta.to(volume.device, torch.float32), spec, size, m, pad)
+    return out[:, 0]
+
+
+def slice_with_pre_affine(volume, nii_affine, pre_affine, fov_mm, fov_vox, is_label=False, pad="global_min"):
+    """Body of the reference's ``nifti_grid_sample`` (affine bookkeeping fused into the sampler).
+
+    volume ``[B,C,D,H,W]``, nii_affine ``[B,4,4]`` fp64, pre_affine ``[B,4,4]`` fp32/fp64,
+    fov_mm (D,H,W) floats (<=0: keep the input FOV), fov_vox (Do,Ho,Wo).
+    Returns ``(out[B,C,Do,Ho,Wo], grid_affine[B,4,4] fp32, nii_affine_out[B,4,4] fp64)``."""
+    L.require_cuda(volume, "volume")
+    dev = volume.device
+    spec = ViewSpec(kind=L.AFFINE_PRE, V=1, nii_affine=_prep(nii_affine, torch.float64, dev),
+                    fov_mm=tuple(float(v) for v in fov_mm))
+    pre = pre_affine.to(dev)
+    if pre.dtype not in (torch.float32, torch.float64):
+        pre = pre.float()
+    out, ga, nii, _ = _run_slice(volume, pre, spec, fov_vox, L.NEAREST if is_label else L.BILINEAR, pad)
+    return out[:, 0], ga[:, 0], nii[:, 0]
+
+
+def acquire_views(x_soft_label, x_label, x_image, nifti_affine, gpre, params, init, *, offset_clip, zoom_clip,
+                  spat, slice_fov_mm, slice_fov_vox, soft_pad="global_min", image_pad="global_min"):
+    """Fused tail of ``AffineTransformModule.forward`` for all views at once.
+
+    x_soft_label ``[B,C,D,H,W]`` float (grad flows), x_label ``[B,C,D,H,W]`` int (nearest, no grad) or None,
+    x_image ``[B,1,D,H,W]`` float (no grad) or None, gpre ``[B,V,4,4]`` fp32, params ``[B,V,6+3R+1]`` fp32
+    (R6 | offset logits | zoom logit: the MLP-head output), init ``[V,10]`` fp32.
+    Returns ``(y_soft[B,V,C,Do,Ho,Wo], y_label, y_image, grid_affine[B,V,4,4], nii_affine[B,V,4,4], theta[B,V,4,4])``.
+    Views are concatenated batch-major, i.e. ``y_soft.flatten(1,2).squeeze(-1)`` is the ``[B, V*C, H, W]`` encoder
+    input the reference builds with ``torch.cat(slices, dim=1)`` (running/run_dl.py:325)."""
+    L.require_cuda(x_soft_label, "x_soft_label")
+    dev = x_soft_label.device
+    B, V = gpre.shape[0], gpre.shape[1]
+    NP = params.shape[-1]
+    R = (NP - 7) // 3
+    spec = ViewSpec(kind=L.AFFINE_PARAMS, V=V, gpre=_prep(gpre, torch.float32, dev).view(B * V, 4, 4),
+                    init=_prep(init, torch.float32, dev), R=R, spat=int(spat), offset_clip=float(offset_clip),
+                    zoom_clip=float(zoom_clip), nii_affine=_prep(nifti_affine, torch.float64, dev),
+                    fov_mm=tuple(float(v) for v in slice_fov_mm))
+    p = params.to(dev, torch.float32).reshape(B * V, NP)
+    y_soft, ga, nii, theta = _run_slice(x_soft_label, p, spec, slice_fov_vox, L.BILINEAR, soft_pad)
+    y_label = y_image = None
+    with torch.no_grad():
+        if x_label is not None and x_label.numel() > 0:
+            y_label = _run_slice(x_label, p.detach(), spec, slice_fov_vox, L.NEAREST, "zero")[0]
+        if x_image is not None and x_image.numel() > 0:
+            y_image = _run_slice(x_image, p.detach(), spec, slice_fov_vox, L.BILINEAR, image_pad)[0]
+    return y_soft, y_label, y_image, ga, nii, theta
+
+
+class _R6Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ortho):
+        L.require_cuda(ortho, "ortho")
+        o = ortho.detach().float().contiguous()
+        N = o.shape[0]
+        mat = torch.empty((N, 4, 4), dtype=torch.float32, device=o.device)
+        with torch.cuda.device(o.device):
+            L.check(L.lib().afb_r6_fwd(L.ptr(o), N, L.ptr(mat), L.stream_ptr(o.device)), "afb_r6_fwd")
+        ctx.save_for_backward(o)
+        ctx.in_dtype = ortho.dtype
+        return mat.to(ortho.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        (o,) = ctx.saved_tensors
+        d = torch.empty_like(o)
+        with torch.cuda.device(o.device):
+            L.check(L.lib().afb_r6_bwd(L.ptr(o), L.ptr(g.float().contiguous()), o.shape[0], L.ptr(d),
+                                       L.stream_ptr(o.device)), "afb_r6_bwd")
+        return d.to(ctx.in_dtype)
+
+
+def r6_to_matrix(ortho: torch.Tensor) -> torch.Tensor:
+    """``compute_rotation_matrix_from_ortho6d`` (utils/transform_utils.py:27-58): [N,6] -> [N,4,4]."""
+    return _R6Fn.apply(ortho)
+
+
+class _EmbedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, affines, V):
+        L.require_cuda(x, "x")
+        xd = x.detach().float().contiguous()
+        ad = affines.detach().to(x.device, torch.float32).contiguous()
+        B, CV, S, _ = xd.shape
+        c = CV // V
+        out = torch.empty((B, CV, S, S, S), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            L.check(L.lib().afb_embed_fwd(L.ptr(xd), L.ptr(ad), B, V, c, S, L.ptr(out), L.stream_ptr(x.device)),
+                    "afb_embed_fwd")
+        ctx.save_for_backward(xd, ad)
+        ctx.V = V
+        ctx.x_dtype, ctx.a_dtype = x.dtype, affines.dtype
+        return out.to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        xd, ad = ctx.saved_tensors
+        V = ctx.V
+        B, CV, S, _ = xd.shape
+        c = CV // V
+        lib = L.lib()
+        need_x, need_a = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (need_x or need_a):
+            return None, None, None
+        with torch.cuda.device(xd.device):
+            dx = torch.zeros_like(xd) if need_x else None
+            da = torch.zeros_like(ad) if need_a else None
+            ws = torch.zeros(int(lib.afb_embed_bwd_workspace_bytes(B * V)), dtype=torch.uint8, device=xd.device)
+            L.check(lib.afb_embed_bwd(L.ptr(g.float().contiguous()), L.ptr(xd), L.ptr(ad), B, V, c, S, L.ptr(dx), L.ptr(da),
+                                      L.ptr(ws), L.stream_ptr(xd.device)), "afb_embed_bwd")
+        return (dx.to(ctx.x_dtype) if dx is not None else None), (da.to(ctx.a_dtype) if da is not None else None), None
+
+
+def embed_slices(x: torch.Tensor, affines: torch.Tensor, n_views: int) -> torch.Tensor:
+    """``SkipConnector.forward`` (models/hybrid_unet.py:71-94).
+
+    x ``[B, V*c, S, S]``, affines ``[V, B, 4, 4]`` (stacked ``b_grid_affines``) -> ``[B, V*c, S, S, S]``."""
+    return _EmbedFn.apply(x, affines, n_views)

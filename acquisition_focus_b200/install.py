@@ -1,0 +1,55 @@
+"""Route an importable ``acquisition_focus`` (the reference) through the B200 kernels.
+
+    import acquisition_focus_b200.install as afb_install
+    afb_install.install()        # after `import acquisition_focus...`
+
+Every reference module on the training hot path that did ``from ...nifti_utils import
+nifti_grid_sample`` holds its own name binding (``models/learnable_transform.py:6``,
+``running/run_dl.py:30``), so each one is patched, as are ``compute_rotation_matrix_from_ortho6d``
+(``models/learnable_transform.py:8``) and ``hybrid_unet.SkipConnector``.  The offline, host-side
+callers (``datasets/base_dataset.py:19``, ``functional/clinical_cardiac_views.py:4``,
+``utils/nnunetv2_utils.py:19``) are deliberately left on the reference's own code: they run once at
+dataset-preparation time on CPU tensors and are outside this path.
+The patched functions accept CUDA tensors only and raise otherwise - there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import sys
+
+from .models.hybrid_unet import SkipConnector
+from .utils.nifti_utils import nifti_grid_sample
+from .utils.transform_utils import compute_rotation_matrix_from_ortho6d
+
+_PATCH_SAMPLE = ["acquisition_focus.models.learnable_transform", "acquisition_focus.running.run_dl"]
+_PATCH_R6 = ["acquisition_focus.models.learnable_transform"]
+
+_originals = {}
+
+
+def install() -> list:
+    """Patch every already-imported hot-path module of the reference; returns what was patched."""
+    done = []
+    for name in _PATCH_SAMPLE:
+        mod = sys.modules.get(name)
+        if mod is not None and hasattr(mod, "nifti_grid_sample"):
+            _originals.setdefault((name, "nifti_grid_sample"), mod.nifti_grid_sample)
+            mod.nifti_grid_sample = nifti_grid_sample
+            done.append(f"{name}.nifti_grid_sample")
+    for name in _PATCH_R6:
+        mod = sys.modules.get(name)
+        if mod is not None and hasattr(mod, "compute_rotation_matrix_from_ortho6d"):
+            _originals.setdefault((name, "compute_rotation_matrix_from_ortho6d"), mod.compute_rotation_matrix_from_ortho6d)
+            mod.compute_rotation_matrix_from_ortho6d = compute_rotation_matrix_from_ortho6d
+            done.append(f"{name}.compute_rotation_matrix_from_ortho6d")
+    mod = sys.modules.get("acquisition_focus.models.hybrid_unet")
+    if mod is not None:
+        _originals.setdefault(("acquisition_focus.models.hybrid_unet", "SkipConnector"), mod.SkipConnector)
+        mod.SkipConnector = SkipConnector
+        done.append("acquisition_focus.models.hybrid_unet.SkipConnector")
+    return done
+
+
+def uninstall() -> None:
+    for (name, attr), fn in _originals.items():
+        setattr(sys.modules[name], attr, fn)
+    _originals.clear()

@@ -1,0 +1,214 @@
+"""Drop-in for the view-parameter tail of the reference's ``models/learnable_transform.py``.
+
+``AffineTransformModule`` keeps the reference's constructor arguments, parameter names
+(``init_theta_ap``, ``init_theta_t_offsets``, ``init_theta_zp``), ``forward`` signature and return
+tuple (reference ``:64-333``).  What changes is where the work happens: the R6 -> rotation,
+soft-argmax offset, tanh zoom, ``T@R@Z``, ``Gpre @ theta`` composition (``:144-230, :262-289``), the
+fp64 NIfTI bookkeeping and the three slicings (``:287-306``) run inside the fused CUDA sampler, and
+their gradients in its backward epilogue.  The LocalizationNet (dense 3-D convolutions, cuDNN) is out
+of scope of this path and is passed in (or a small default is built).
+
+``ATModulesContainer.acquire`` additionally slices ALL views of a batch in one launch
+(B x V slices), which is what ``running/run_dl.py:283-312`` loops over in Python.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from .. import functional as AF
+from ..synthetic import random_aug_affine
+from ..utils.nifti_utils import nifti_grid_sample
+
+
+class DefaultLocalizationNet(nn.Module):
+    """Small 3-D conv encoder + linear head producing ``[B, 6 + 3R + 1]`` (placeholder for the reference's
+    LocalizationNet, ``models/learnable_transform.py:38-60``; any module with that output works)."""
+
+    def __init__(self, input_channels: int, output_size: int, size_3d: Sequence[int]):
+        super().__init__()
+        self.conv_net = nn.Sequential(
+            nn.Conv3d(input_channels, 16, 5, stride=2, padding=2), nn.InstanceNorm3d(16), nn.LeakyReLU(),
+            nn.Conv3d(16, 32, 3, stride=2, padding=1), nn.InstanceNorm3d(32), nn.LeakyReLU(),
+            nn.Conv3d(32, 32, 3, stride=2, padding=1), nn.InstanceNorm3d(32), nn.LeakyReLU(),
+            nn.AdaptiveAvgPool3d(2))
+        self.fc = nn.Linear(32 * 8, output_size)
+        nn.init.zeros_(self.fc.weight)
+        nn.init.zeros_(self.fc.bias)
+
+    def forward(self, x):
+        return self.fc(self.conv_net(x).flatten(1))
+
+
+class AffineTransformModule(nn.Module):
+    def __init__(self, input_channels, volume_fov_mm, volume_fov_vox, slice_fov_mm, slice_fov_vox,
+                 optim_method="angle-axis", use_affine_theta=True, offset_clip_value=1.0, zoom_clip_value=2.0,
+                 view_id=None, align_corners=False, rotate_slice_to_min_principle=False, localization_net=None):
+        super().__init__()
+        assert volume_fov_mm[0] == volume_fov_mm[1] == volume_fov_mm[2]
+        assert volume_fov_vox[0] == volume_fov_vox[1] == volume_fov_vox[2]
+        assert optim_method in ["angle-axis", "normal-vector", "R6-vector"], \
+            f"optim_method must be 'angle-axis', 'normal-vector' or 'R6-vector', not {optim_method}"
+        if optim_method != "R6-vector":
+            raise NotImplementedError("only the default 'R6-vector' parameterisation is on the CUDA path")
+        if align_corners or rotate_slice_to_min_principle:
+            raise NotImplementedError("align_corners / rotate_slice_to_min_principle are off in the reference "
+                                      "defaults and not part of the accelerated path")
+        self.optim_method = optim_method
+        self.ap_space = 6
+        self.init_theta_ap = nn.Parameter(torch.tensor([[1e-2, 0, 0, 0, 1e-2, 0]]), requires_grad=False)
+        self.volume_fov_mm = torch.as_tensor(volume_fov_mm)
+        self.volume_fov_vox = torch.as_tensor(volume_fov_vox)
+        self.slice_fov_vox = torch.as_tensor(slice_fov_vox)
+        self.slice_fov_mm = torch.as_tensor(slice_fov_mm)
+        self.use_affine_theta = use_affine_theta
+        self.align_corners = align_corners
+        self.rotate_slice_to_min_principle = rotate_slice_to_min_principle
+        self.offset_clip_value = float(offset_clip_value)
+        self.zoom_clip_value = float(zoom_clip_value)
+        self.spat = int(self.volume_fov_vox[0])
+        # vox_range / arra: width of the soft-argmax support in voxels (reference :112-116)
+        self.vox_range = int(round(self.get_vox_offsets_from_gs_offsets(self.offset_clip_value)
+                                   - self.get_vox_offsets_from_gs_offsets(-self.offset_clip_value)))
+        self.arra = torch.arange(0, self.vox_range) + (self.spat - self.vox_range) // 2
+        out_size = self.ap_space + 3 * self.vox_range + 1
+        self.localization_net = localization_net if localization_net is not None else \
+            DefaultLocalizationNet(input_channels, out_size, [int(v) for v in self.volume_fov_vox])
+        self.view_id = view_id
+        self.init_theta_t_offsets = nn.Parameter(torch.zeros([3]), requires_grad=False)
+        self.init_theta_zp = nn.Parameter(torch.ones([1, 1]), requires_grad=False)
+        self.last_theta = None
+        self.last_grid_affine = None
+        self.last_transformed_nifti_affine = None
+        self.random_grid_affine = random_aug_affine(torch.Generator().manual_seed(torch.seed() % (2 ** 31)),
+                                                    rotation_strength=4.0, zoom_strength=0.0)[None]
+
+    # -- same small API as the reference ---------------------------------------------------------
+    def set_init_theta_ap(self, init_theta_ap):
+        self.init_theta_ap.data = init_theta_ap.data
+
+    def set_init_theta_t_offsets(self, init_theta_t_offsets):
+        self.init_theta_t_offsets.data = init_theta_t_offsets.data
+
+    def set_init_theta_zp(self, init_theta_zp):
+        self.init_theta_zp.data = init_theta_zp.data
+
+    def get_vox_offsets_from_gs_offsets(self, gs_offsets):
+        return ((gs_offsets + 1.0) * self.spat - 1.0) / 2.0
+
+    def init_vector(self) -> torch.Tensor:
+        """``[10]``: init_theta_ap | init_theta_t_offsets | init_theta_zp, the layout afb_views.init wants."""
+        return torch.cat([self.init_theta_ap.reshape(6).float(), self.init_theta_t_offsets.reshape(3).float(),
+                          self.init_theta_zp.reshape(1).float()])
+
+    def get_init_affines(self):
+        """Init rotation / translation / zoom 4x4s (reference :144-161); host-side convenience."""
+        dev = self.init_theta_t_offsets.device
+        if dev.type == "cuda":
+            theta_a = AF.r6_to_matrix(self.init_theta_ap.view(1, 6))
+        else:
+            raise RuntimeError("get_init_affines needs the module on a CUDA device (no CPU fallback)")
+        theta_t = torch.eye(4, device=dev)[None].clone()
+        theta_t[0, :3, 3] = self.init_theta_t_offsets
+        z = self.init_theta_zp.view(1)
+        theta_z = torch.diag_embed(torch.cat([z, z, z, torch.ones(1, device=dev)]))[None]
+        return theta_a.float(), theta_t.float(), theta_z.float()
+
+    def mlp_head(self, x_soft_label, nifti_affine, grid_affine_pre_mlp):
+        """LocalizationNet input (pre-oriented prescan volume, reference :248-255) -> ``[B, 6+3R+1]``."""
+        with torch.no_grad():
+            x_pre, _, _ = nifti_grid_sample(x_soft_label, nifti_affine, target_fov_mm=self.volume_fov_mm,
+                                            target_fov_vox=self.volume_fov_vox, is_label=False,
+                                            pre_grid_sample_affine=grid_affine_pre_mlp)
+        return self.localization_net(x_pre)
+
+    def forward(self, x_soft_label, x_label, x_image, nifti_affine, grid_affine_pre_mlp, theta_override=None):
+        soft_none = x_soft_label is None or x_soft_label.numel() == 0
+        assert not soft_none
+        B = x_soft_label.shape[0]
+        dev = x_soft_label.device
+        gpre = grid_affine_pre_mlp.to(dev, torch.float32)
+        if theta_override is not None or not self.use_affine_theta:
+            if theta_override is not None:
+                theta = theta_override.detach().clone().to(dev, torch.float32)       # non-differentiable (:260)
+            else:
+                a, t, z = self.get_init_affines()
+                theta = (t @ a @ z).repeat(B, 1, 1)
+            self.last_theta = theta
+            pre = gpre @ theta
+            kw = dict(target_fov_mm=self.slice_fov_mm, target_fov_vox=self.slice_fov_vox, pre_grid_sample_affine=pre)
+            y_soft, grid_affine, nii = nifti_grid_sample(x_soft_label, nifti_affine, is_label=False, **kw)
+            y_label = y_image = None
+            with torch.no_grad():
+                if x_label is not None and x_label.numel() > 0:
+                    y_label = nifti_grid_sample(x_label, nifti_affine, is_label=True, **kw)[0]
+                if x_image is not None and x_image.numel() > 0:
+                    y_image = nifti_grid_sample(x_image, nifti_affine, is_label=False, **kw)[0]
+        else:
+            mlp_out = self.mlp_head(x_soft_label, nifti_affine, gpre)
+            y_soft, y_label, y_image, grid_affine, nii, theta = AF.acquire_views(
+                x_soft_label, x_label, x_image, nifti_affine, gpre[:, None], mlp_out[:, None], self.init_vector()[None],
+                offset_clip=self.offset_clip_value, zoom_clip=self.zoom_clip_value, spat=self.spat,
+                slice_fov_mm=self.slice_fov_mm.tolist(), slice_fov_vox=self.slice_fov_vox.tolist())
+            y_soft, grid_affine, nii, theta = y_soft[:, 0], grid_affine[:, 0], nii[:, 0], theta[:, 0]
+            y_label = None if y_label is None else y_label[:, 0]
+            y_image = None if y_image is None else y_image[:, 0]
+            self.last_theta = theta
+        self.last_grid_affine = grid_affine
+        self.last_transformed_nifti_affine = nii
+        return y_soft, y_label, y_image, grid_affine, nii
+
+
+class ATModulesContainer(nn.ModuleList):
+    """One AffineTransformModule per base view (reference :370-414) + a fused all-views acquisition."""
+
+    def __init__(self, config, num_classes, localization_net_factory=None):
+        super().__init__()
+        for view_id in config.base_views:
+            self.add_new_atm(view_id, config, num_classes, localization_net_factory)
+        self.is_optimized = nn.Parameter(torch.tensor(len(config.base_views) * [False]), requires_grad=False)
+
+    def add_new_atm(self, view_id, config, num_classes, localization_net_factory=None):
+        net = localization_net_factory() if localization_net_factory is not None else None
+        self.append(AffineTransformModule(
+            num_classes, torch.tensor(config.prescan_fov_mm), torch.tensor(config.prescan_fov_vox),
+            torch.tensor(config.slice_fov_mm), torch.tensor(config.slice_fov_vox),
+            offset_clip_value=config.offset_clip_value, zoom_clip_value=config.zoom_clip_value,
+            optim_method=config.affine_theta_optim_method, view_id=view_id,
+            rotate_slice_to_min_principle=config.rotate_slice_to_min_principle, localization_net=net))
+
+    def state_dict(self, *args, **kwargs):
+        sd = super().state_dict(*args, **kwargs)
+        sd.update({"is_optimized": self.get_active_views()})
+        return sd
+
+    def get_all_atms_requires_grad(self):
+        return torch.tensor([next(atm.localization_net.parameters()).requires_grad for atm in self])
+
+    def get_active_views(self):
+        return self.is_optimized.cpu() | self.get_all_atms_requires_grad()
+
+    def get_active_view_modules(self):
+        return [m for m, a in zip(self, self.get_active_views()) if a]
+
+    def acquire(self, x_soft_label, x_label, x_image, nifti_affine, view_pre_affines, mlp_outs: Optional[list] = None):
+        """All views in ONE launch per volume kind.  ``view_pre_affines``: list (len V) of ``[B,4,4]``;
+        ``mlp_outs``: optional list of ``[B, 6+3R+1]`` (else each module's LocalizationNet is run).
+        Returns ``(y_soft[B,V,C,H,W,1], y_label, y_image, grid_affines[B,V,4,4], nii[B,V,4,4])``."""
+        atms = list(self)
+        dev = x_soft_label.device
+        gpre = torch.stack([g.to(dev, torch.float32) for g in view_pre_affines], dim=1)
+        if mlp_outs is None:
+            mlp_outs = [m.mlp_head(x_soft_label, nifti_affine, g) for m, g in zip(atms, view_pre_affines)]
+        params = torch.stack(mlp_outs, dim=1)
+        init = torch.stack([m.init_vector() for m in atms]).to(dev)
+        a0 = atms[0]
+        y_soft, y_label, y_image, ga, nii, theta = AF.acquire_views(
+            x_soft_label, x_label, x_image, nifti_affine, gpre, params, init, offset_clip=a0.offset_clip_value,
+            zoom_clip=a0.zoom_clip_value, spat=a0.spat, slice_fov_mm=a0.slice_fov_mm.tolist(),
+            slice_fov_vox=a0.slice_fov_vox.tolist())
+        for v, m in enumerate(atms):
+            m.last_theta, m.last_grid_affine, m.last_transformed_nifti_affine = theta[:, v], ga[:, v], nii[:, v]
+        return y_soft, y_label, y_image, ga, nii

@@ -1,0 +1,163 @@
+/* afb200.h - C ABI of libafb200.so: B200 (sm_100a) kernels for the differentiable
+ * view-acquisition hot path of multimodallearning/acquisition-focus.
+ *
+ * The reference has no FFI layer of its own: the path is pure Python over torch ATen.  The
+ * boundary this library replaces is therefore the set of ATen calls the reference makes
+ * (paths relative to /root/reference/acquisition_focus):
+ *
+ *   utils/nifti_utils.py:36-71    fp64 affine bookkeeping (grid affine + NIfTI affine)
+ *   utils/nifti_utils.py:182-184  F.affine_grid
+ *   utils/nifti_utils.py:87-94    F.grid_sample (checkpointed), bilinear / nearest
+ *   utils/nifti_utils.py:200-203  min-shift  (volume - min, + min)
+ *   utils/transform_utils.py:27-58            R6 -> rotation matrix
+ *   models/learnable_transform.py:144-230     init / batch affines (R6, soft-argmax offset, tanh zoom)
+ *   models/learnable_transform.py:262-289     theta = T@R@Z, pre = Gpre @ theta
+ *   models/hybrid_unet.py:71-94               SkipConnector: slice -> 3-D embedding
+ *   + the autograd of all of the above.
+ *
+ * Conventions
+ *   - every entry point returns int: 0 = ok, >0 = cudaError_t of the launch, <0 = AFB_E* argument error
+ *   - all data pointers are CALLER-OWNED DEVICE pointers unless marked "host"; the library
+ *     allocates nothing and keeps no state; work is enqueued on `stream` and is asynchronous
+ *   - one device per call (the caller sets the current device); re-entrant, thread-safe
+ *   - tensors are row-major; volume strides are in ELEMENTS; (D,H,W) index order throughout,
+ *     torch grid convention for affines (x->W, y->H, z->D, normalised [-1,1], align_corners=False)
+ *   - slices are ordered [b][v] (batch-major): slice s = b*V + v
+ */
+#ifndef AFB200_H
+#define AFB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AFB_VERSION 100
+
+/* error codes (negative) */
+#define AFB_OK 0
+#define AFB_EINVAL (-1)      /* bad argument (null pointer, non-positive size, bad enum) */
+#define AFB_EDTYPE (-2)      /* dtype/mode combination not supported */
+#define AFB_ESHAPE (-3)      /* inconsistent shapes */
+#define AFB_EUNSUPPORTED (-4)
+
+/* storage dtypes */
+#define AFB_F32 0
+#define AFB_BF16 1
+#define AFB_F16 2
+#define AFB_I64 3
+#define AFB_I32 4
+#define AFB_I16 5
+#define AFB_U8 6
+
+/* interpolation (F.grid_sample mode; padding_mode='zeros', align_corners=False always) */
+#define AFB_BILINEAR 0
+#define AFB_NEAREST 1
+
+/* out-of-bounds value of the bilinear path.  The reference shifts by the global minimum of the
+ * tensor passed in one call (nifti_utils.py:200-203), so out-of-bounds evaluates to min(volume). */
+#define AFB_PAD_ZERO 0      /* plain grid_sample zeros padding */
+#define AFB_PAD_VALUE 1     /* host-supplied value (e.g. 0 for one-hot volumes)            */
+#define AFB_PAD_DEVICE 2    /* value read from a device float (output of afb_volume_min)   */
+
+/* how the per-slice grid affine is obtained (fused prologue of the sampler) */
+#define AFB_AFFINE_GRID 0   /* theta[S,3,4] fp32 used as is (F.affine_grid input)                         */
+#define AFB_AFFINE_PRE 1    /* pre_grid_sample_affine P[S,4,4] -> nifti_utils.py:36-58                    */
+#define AFB_AFFINE_PARAMS 2 /* raw view parameters -> learnable_transform.py:144-230,262-289 -> PRE path  */
+
+typedef struct afb_volume {
+    const void* data;       /* [B,C,D,H,W] with arbitrary element strides */
+    int dtype;              /* AFB_F32 ... */
+    int B, C, D, H, W;
+    int64_t sB, sC, sD, sH, sW;
+} afb_volume;
+
+typedef struct afb_views {
+    int kind;               /* AFB_AFFINE_* */
+    int V;                  /* views per volume; S = B*V slices, slice s = b*V + v */
+    /* AFB_AFFINE_GRID */
+    const float* theta;     /* [S,3,4] */
+    /* AFB_AFFINE_PRE */
+    const void* pre;        /* [S,4,4] fp32 or fp64 */
+    int pre_is_f64;
+    /* AFB_AFFINE_PARAMS: per slice [R6(6) | offset logits (3*R) | zoom logit (1)] (MLP-head output) */
+    const float* params;    /* [S, 6+3R+1] */
+    const float* gpre;      /* [S,4,4] fp32 grid_affine_pre_mlp (clinical view affine incl. augmentation) */
+    const float* init;      /* [V,10]: init_theta_ap[6], init_theta_t_offsets[3], init_theta_zp[1]        */
+    int R;                  /* vox_range = round(offset_clip*spat), learnable_transform.py:112-115        */
+    int spat;               /* volume_fov_vox[0], learnable_transform.py:110                              */
+    float offset_clip;      /* 0 => offsets forced to 0 (learnable_transform.py:211-212)                  */
+    float zoom_clip;
+    /* PRE and PARAMS: NIfTI bookkeeping inputs */
+    const double* nii_affine;   /* [B,4,4] fp64 (NULL => identity; only ratios/zooms of it are used)      */
+    double fov_mm[3];           /* host: target_fov_mm in (D,H,W) order; <=0 => input FOV (nifti_utils.py:140) */
+} afb_views;
+
+/* ---- library info -------------------------------------------------------------------------- */
+int afb_version(void);
+const char* afb_error_string(int code);
+
+/* ---- min pre-pass of the bilinear path (nifti_utils.py:200) -------------------------------- */
+/* Scans n_elements of a dense tensor; writes out_min_count[0] = min as float32,
+ * out_min_count[1] = number of elements equal to the min (as float32, exact < 2^24, else rounded).
+ * workspace: >= afb_volume_min_workspace_bytes() bytes, contents arbitrary. */
+int64_t afb_volume_min_workspace_bytes(void);
+int afb_volume_min(const void* data, int dtype, int64_t n_elements, float* out_min_count,
+                   void* workspace, void* stream);
+
+/* ---- slice / volume extraction, forward ------------------------------------------------------
+ * out[b, v, c, i, j, k] for (i,j,k) in (Do,Ho,Wo); out dtype = volume dtype.
+ * grid_affine_out [S,4,4] fp32 (G', what nifti_grid_sample returns; NULL allowed),
+ * nii_affine_out  [S,4,4] fp64 (NIfTI affine of the resampled array; NULL allowed; PRE/PARAMS only),
+ * theta_out       [S,4,4] fp32 (PARAMS only: theta = T@R@Z, `last_theta`; NULL allowed).          */
+int afb_slice_fwd(const afb_volume* vol, const afb_views* views, int Do, int Ho, int Wo, int mode,
+                  int pad_mode, float pad_value, const float* pad_device, void* out,
+                  float* grid_affine_out, double* nii_affine_out, float* theta_out, void* stream);
+
+/* ---- slice extraction, backward (bilinear only) ----------------------------------------------
+ * grad_out         [S,C,Do,Ho,Wo] fp32 contiguous; NULL => chain-only (only grad_grid_affine is
+ *                  propagated to d_affine; used for nearest / integer volumes)
+ * grad_grid_affine [S,4,4] fp32 or NULL: upstream gradient w.r.t. the returned grid_affine_out
+ * d_vol            fp32, SAME element strides as the volume, pre-zeroed by the caller, or NULL
+ *                  (training case: the volume never requires grad)
+ * d_affine         gradient w.r.t. the view input of `views->kind`:
+ *                    GRID   -> [S,3,4]   PRE -> [S,4,4]   PARAMS -> [S, 6+3R+1]        (fp32)
+ * d_gpre           PARAMS only, [S,4,4] fp32 or NULL
+ * d_pad            device float accumulator (+=) of d(out)/d(pad value) = sum go*(1-sum w_inbounds),
+ *                  or NULL; the caller zeroes it.  Feeds afb_min_grad (MinBackward of the reference).
+ * workspace        >= afb_slice_bwd_workspace_bytes(S) bytes, ZEROED by the caller before the first
+ *                  use; the kernel leaves it zeroed again on completion.                            */
+int64_t afb_slice_bwd_workspace_bytes(int S);
+int afb_slice_bwd(const afb_volume* vol, const afb_views* views, int Do, int Ho, int Wo,
+                  int pad_mode, float pad_value, const float* pad_device,
+                  const float* grad_out, const float* grad_grid_affine,
+                  float* d_vol, float* d_affine, float* d_gpre, float* d_pad,
+                  void* workspace, void* stream);
+
+/* MinBackward of `volume.min()` (evenly distributed over all elements equal to the min):
+ * d_vol[i] += (vol[i] == min) * d_pad / count.  vol dense (any permutation), d_vol same layout. */
+int afb_min_grad(const void* vol, int dtype, int64_t n_elements, const float* min_count,
+                 const float* d_pad, float* d_vol, void* stream);
+
+/* ---- R6 -> rotation (utils/transform_utils.py:27-58) ------------------------------------------ */
+int afb_r6_fwd(const float* ortho /*[N,6]*/, int N, float* mat /*[N,4,4]*/, void* stream);
+int afb_r6_bwd(const float* ortho, const float* grad_mat /*[N,4,4]*/, int N, float* d_ortho /*[N,6]*/,
+               void* stream);
+
+/* ---- slice -> 3-D embedding (models/hybrid_unet.py:71-94) -------------------------------------
+ * x        [B, V*c, S, S] fp32 contiguous (view-major channels, as torch.chunk(dim=1))
+ * affines  [V, B, 4, 4] fp32: the slicing grid affines (b_grid_affines stacked)
+ * out      [B, V*c, S, S, S] fp32
+ * Backward: d_x [B,V*c,S,S] and d_affines [V,B,4,4] (either may be NULL); d_x must be pre-zeroed.
+ * workspace: >= afb_embed_bwd_workspace_bytes(B*V), zeroed before first use, left zeroed.        */
+int afb_embed_fwd(const float* x, const float* affines, int B, int V, int c, int S, float* out,
+                  void* stream);
+int64_t afb_embed_bwd_workspace_bytes(int n_slices);
+int afb_embed_bwd(const float* grad_out, const float* x, const float* affines, int B, int V, int c,
+                  int S, float* d_x, float* d_affines, void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFB200_H */

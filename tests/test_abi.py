@@ -1,0 +1,61 @@
+"""CPU-side checks of the boundary: the library builds for sm_100a, loads, and exports every symbol the
+header declares (no compute calls without a GPU); the product refuses CPU tensors."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_build_and_exports():
+    from acquisition_focus_b200 import build, _lib
+    path = build.build()
+    assert os.path.exists(path)
+    lib = _lib.lib()
+    header = open(os.path.join(ROOT, "include", "afb200.h")).read()
+    declared = set(re.findall(r"\b(afb_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in afb200.h but not exported"
+    assert declared == set(_lib.exported_symbols())
+    assert lib.afb_version() == int(re.search(r"#define AFB_VERSION (\d+)", header).group(1))
+    assert lib.afb_error_string(-1).decode().startswith("invalid argument")
+
+
+def test_struct_layout_matches_header():
+    import ctypes as C
+    from acquisition_focus_b200 import _lib
+    assert C.sizeof(_lib.AfbVolume) == 8 + 4 * 6 + 8 * 5
+    # afb_views: 2 int, 2 ptr, int(+pad), 3 ptr, 2 int, 2 float, ptr, 3 double
+    assert C.sizeof(_lib.AfbViews) == 8 + 16 + 8 + 24 + 8 + 8 + 8 + 24
+
+
+def test_argument_errors_without_gpu():
+    from acquisition_focus_b200 import _lib
+    lib = _lib.lib()
+    assert lib.afb_slice_fwd(None, None, 1, 1, 1, 0, 0, 0.0, None, None, None, None, None, None) == -1
+    assert lib.afb_embed_fwd(None, None, 1, 1, 1, 4, None, None) == -1
+    assert lib.afb_r6_fwd(None, 1, None, None) == -1
+    assert lib.afb_volume_min(None, 0, 10, None, None, None) == -1
+
+
+def test_no_cpu_fallback():
+    import acquisition_focus_b200 as afb
+    from acquisition_focus_b200._lib import AfbError
+    with pytest.raises(AfbError):
+        afb.nifti_grid_sample(torch.zeros(1, 1, 4, 4, 4), torch.eye(4)[None].double())
+    with pytest.raises(AfbError):
+        afb.compute_rotation_matrix_from_ortho6d(torch.randn(2, 6))
+    with pytest.raises(AfbError):
+        afb.SkipConnector(1)(torch.zeros(1, 1, 4, 4), [torch.eye(4)[None]])
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "acquisition_focus_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
