@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py - slices/sec of the differentiable view-acquisition hot path (fwd + bwd, 128^3 -> 128^2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--volumes NV] [--views V]
+
+One "step" = one pass of the hot path over one batch of synthetic input, with the reference's exact
+semantics (BASELINE.json configs[1] content at configs[3] scale):
+
+    per GPU: NV volumes x V views;  per volume an 8-class one-hot soft label [8,128^3] fp32 (bilinear, WITH
+    gradient w.r.t. the volume and the view parameters), the same one-hot as int64 (nearest) and a 1-channel
+    fp32 image (bilinear), all sliced to 128x128x1 from raw view parameters (R6 | 3x26 offset logits | zoom)
+    composed with an augmented p2CH clinical affine:
+      min pass (volume.min() of the reference's min-shift) -> fused-prologue slice forward x3 ->
+      backward (dVolume scatter + dTheta reduce + analytic parameter chain) -> MinBackward pass
+      -> [N>1] one NCCL all-reduce of the [V,85] view-parameter gradients.
+
+`value`  : slices/s with inputs resident in HBM (device timed, CUDA events, max over ranks).
+`e2e`    : same metric through the public API from HOST buffers: pinned index-label + image volumes are copied
+           H2D inside the timed region, expanded to one-hot on the device (as running/run_dl.py:261-264 does),
+           and the reduced parameter gradients + grid affines are read back D2H every step.
+`--impl reference` times the oracle port of the reference's own torch-CPU path on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+NUM_CLASSES = 8
+S = 128
+OFFSET_CLIP, ZOOM_CLIP = 0.2, 0.0
+R = 26                                  # round(0.2 * 128), models/learnable_transform.py:112-115
+NP = 6 + 3 * R + 1
+METRIC = "slices/sec (fwd+bwd 128^3->128^2 sampling)"
+UNIT = "slices/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--volumes", type=int, default=64, help="volumes per GPU (weak scaling)")
+    ap.add_argument("--views", type=int, default=6)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-breakdown", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic inputs
+# ------------------------------------------------------------------------------------------------
+def make_host_inputs(nv: int, views: int, seed: int):
+    """Index-label volumes [nv,128^3] int64 + image [nv,1,128^3] fp32 on the host, view parameters."""
+    from acquisition_focus_b200 import synthetic as syn
+    base = syn.heart_phantom(S)
+    rng = np.random.default_rng(seed)
+    variants = [base, np.ascontiguousarray(base.transpose(1, 0, 2)[::-1]), np.ascontiguousarray(base[:, ::-1, :]),
+                np.ascontiguousarray(base.transpose(2, 1, 0)), np.ascontiguousarray(base[::-1, :, ::-1])]
+    lab = np.stack([np.roll(variants[i % len(variants)], int(rng.integers(-6, 7)), axis=int(rng.integers(0, 3)))
+                    for i in range(nv)])
+    means = np.array([0.05, 0.55, 0.85, 0.95, 0.80, 0.90, 0.75, 0.70], dtype=np.float32)
+    img = means[lab] + 0.15 * rng.standard_normal(lab.shape, dtype=np.float32)
+    gen = torch.Generator().manual_seed(seed)
+    p2ch = syn.phantom_view_affines()["p2CH"]
+    gpre = torch.stack([torch.stack([p2ch @ syn.random_aug_affine(gen, 0.1, 0.2, 0.0) for _ in range(views)])
+                        for _ in range(nv)])                                   # [nv,V,4,4]
+    r6 = torch.tensor([1.0, 0, 0, 0, 1.0, 0]) + 0.3 * torch.randn(nv, views, 6, generator=gen)
+    params = torch.cat([r6, torch.randn(nv, views, 3 * R, generator=gen), torch.randn(nv, views, 1, generator=gen)], dim=-1)
+    init = torch.tensor([[1e-2, 0, 0, 0, 1e-2, 0, 0, 0, 0, 1.0]]).repeat(views, 1)
+    nii = syn.default_nifti_affine(nv, 1.5)
+    return dict(lab=torch.from_numpy(lab), img=torch.from_numpy(img)[:, None], gpre=gpre, params=params, init=init, nii=nii)
+
+
+def one_hot_volumes(lab):
+    """running/run_dl.py:261-264: one-hot (channels-last view) and its float copy."""
+    oh = torch.nn.functional.one_hot(lab, NUM_CLASSES).permute(0, 4, 1, 2, 3)
+    return oh, oh.float()
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: oracle port of the reference's torch-CPU path
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step(h, b0, b1, views, go):
+    from oracle import af_oracle as O
+    lab = h["lab"][b0:b1]
+    label, soft = one_hot_volumes(lab)
+    soft = soft.requires_grad_(True)
+    params = h["params"][b0:b1].clone().requires_grad_(True)
+    fov_mm, fov_vox = torch.tensor([192.0, 192.0, 1.5]), torch.tensor([S, S, 1])
+    loss = 0
+    for v in range(views):
+        theta = O.view_theta(params[:, v], h["init"][v:v + 1, :6], h["init"][v, 6:9], h["init"][v:v + 1, 9:],
+                             OFFSET_CLIP, ZOOM_CLIP, S)
+        ys, yl, yi, ga, nii = O.atm_tail_forward(soft, label, h["img"][b0:b1], h["nii"][b0:b1], h["gpre"][b0:b1, v], theta,
+                                                 fov_mm, fov_vox)
+        loss = loss + (ys * go[: b1 - b0, v]).sum()
+    loss.backward()
+    return params.grad.sum(0)
+
+
+def time_cpu_reference(h, views, vols_per_step, budget_s, min_steps=1, warmup=1, steps=None):
+    torch.set_num_threads(os.cpu_count() or 1)
+    go = torch.from_numpy(np.cos(np.arange(vols_per_step * views * NUM_CLASSES * S * S, dtype=np.float64) * 0.618).astype(np.float32)
+                          ).view(vols_per_step, views, NUM_CLASSES, S, S, 1)
+    for _ in range(warmup):
+        cpu_reference_step(h, 0, vols_per_step, views, go)
+    times = []
+    t_start = time.perf_counter()
+    while True:
+        t0 = time.perf_counter()
+        cpu_reference_step(h, 0, vols_per_step, views, go)
+        times.append(time.perf_counter() - t0)
+        if steps is not None:
+            if len(times) >= steps:
+                break
+        elif len(times) >= min_steps and time.perf_counter() - t_start > budget_s:
+            break
+    return times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    views, vps = args.views, 2
+    h = make_host_inputs(vps, views, seed=0)
+    times = time_cpu_reference(h, views, vps, budget_s=0, warmup=max(1, min(args.warmup, 1)), steps=max(1, args.steps))
+    ms = float(np.mean(times)) * 1e3
+    val = vps * views / (ms / 1e3)
+    cores = os.cpu_count() or 1
+    sample = f"{vps} volumes x {views} views (cfg2 content: soft C=8 grad + int64 one-hot label + image) per step"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+            "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, note="reference arm: oracle port of the reference's torch-CPU path, bounded sample"),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, note=""):
+    return {"workload": f"cfg4 throughput sweep with cfg2 content: {args.volumes} volumes x {args.views} views per GPU (weak "
+                        f"scaling), 128^3 -> 128x128x1, soft label C=8 fp32 one-hot (grad wrt volume+params) + int64 one-hot "
+                        f"label (nearest) + image C=1, raw R6/offset/zoom params composed with augmented p2CH affine",
+            "volumes_per_gpu": args.volumes, "views": args.views, "slice": [S, S, 1], "volume": [S, S, S],
+            "l2_policy": "inputs larger than L2 (>=4 GiB per tensor at 64 volumes); no explicit flush",
+            "note": note}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = [r.split(",") for r in open(self.tmp.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.tmp.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].strip().lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import acquisition_focus_b200 as afb
+    from acquisition_focus_b200 import functional as AF
+    from acquisition_focus_b200 import parallel as par
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    nv, V = args.volumes, args.views
+    h = make_host_inputs(nv, V, seed=1000 + rank)
+    host_lab = h["lab"].pin_memory()
+    host_img = h["img"].pin_memory()
+
+    lab_d = host_lab.to(dev)
+    label, soft = one_hot_volumes(lab_d)
+    del lab_d
+    image = host_img.to(dev)
+    nii, gpre, init = h["nii"].to(dev), h["gpre"].to(dev), h["init"].to(dev)
+    params = h["params"].to(dev).requires_grad_(True)
+    soft.requires_grad_(True)
+    go = torch.cos(torch.arange(nv * V * NUM_CLASSES * S * S, device=dev, dtype=torch.float32) * 0.618).view(nv, V, NUM_CLASSES, S, S, 1)
+    fov_mm, fov_vox = [192.0, 192.0, 1.5], [S, S, 1]
+    LAUNCHES_PER_STEP = 7      # volume_min x2, slice_fwd x3, slice_bwd, min_grad
+
+    def step(soft_t, label_t, image_t):
+        soft_t.grad = None
+        params.grad = None
+        pad_s = AF.volume_min(soft_t)
+        pad_i = AF.volume_min(image_t)
+        ys, yl, yi, ga, nii_o, theta = AF.acquire_views(soft_t, label_t, image_t, nii, gpre, params, init, offset_clip=OFFSET_CLIP,
+                                                        zoom_clip=ZOOM_CLIP, spat=S, slice_fov_mm=fov_mm, slice_fov_vox=fov_vox,
+                                                        soft_pad=pad_s, image_pad=pad_i)
+        torch.autograd.backward([ys], [go])
+        g = par.reduce_view_grads(params.grad)          # [V,NP]; NCCL all-reduce when world > 1
+        return g, ga
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(max(3, args.warmup)):
+        step(soft, label, image)
+    sync_all()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        step(soft, label, image)
+    e1.record()
+    sync_all()
+    elapsed_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
+    clk = clocks.stop() if rank == 0 else None
+    ms_per_step = elapsed_ms.item() / args.steps
+    value = world * nv * V / (ms_per_step / 1e3)
+
+    # ---- e2e: host buffers -> H2D -> one-hot on device -> step -> D2H of reduced grads + grid affines ----
+    g_host = torch.empty((V, NP), dtype=torch.float32).pin_memory()
+    ga_host = torch.empty((nv, V, 4, 4), dtype=torch.float32).pin_memory()
+    h2d = host_lab.numel() * host_lab.element_size() + host_img.numel() * host_img.element_size()
+    d2h = g_host.numel() * 4 + ga_host.numel() * 4
+
+    def e2e_step():
+        lab_dev = host_lab.to(dev, non_blocking=True)
+        img_dev = host_img.to(dev, non_blocking=True)
+        label_t, soft_t = one_hot_volumes(lab_dev)
+        soft_t.requires_grad_(True)
+        g, ga = step(soft_t, label_t, img_dev)
+        g_host.copy_(g, non_blocking=True)
+        ga_host.copy_(ga.detach(), non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+
+    del soft, label
+    torch.cuda.empty_cache()
+    e2e_step()
+    sync_all()
+    e0.record()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    e1.record()
+    sync_all()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * nv * V / (e2e_ms.item() / args.e2e_steps / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel breakdown + roofline (rank 0, after the timed regions) ----
+    lab_d = host_lab.to(dev)
+    label, soft = one_hot_volumes(lab_d)
+    del lab_d
+    soft.requires_grad_(True)
+    breakdown, roofline, l2_gbs = ({}, None, None)
+    if not args.no_breakdown:
+        breakdown, l2_gbs = kernel_breakdown(AF, dev, soft, label, image, nii, gpre, params, init, go, fov_mm, fov_vox, nv, V)
+        roofline = make_roofline(breakdown, l2_gbs)
+
+    cpu_base = None
+    if world == 1 and not args.no_cpu_baseline:
+        vps = 2
+        times = time_cpu_reference(h, V, vps, budget_s=args.cpu_seconds, min_steps=2)
+        cval = vps * V / float(np.mean(times))
+        cpu_base = {"value": cval, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                    "sample": f"{vps} volumes x {V} views of the same workload per step, {len(times)} steps after 1 warm-up "
+                              f"(oracle port of the reference's torch-CPU path, torch.set_num_threads(all cores))"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args), "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": args.e2e_steps,
+                    "what": "pinned host index-label int64 + image fp32 -> H2D -> device one-hot -> same step -> D2H reduced dTheta + grid affines"},
+            "gpu_launches": LAUNCHES_PER_STEP * args.steps, "roofline": roofline, "cpu_baseline": cpu_base,
+            "kernels": breakdown, "l2_gbs_measured": l2_gbs}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _time(fn, dev, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize(dev)
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize(dev)
+        ts.append(a.elapsed_time(b))
+    return float(np.mean(ts))
+
+
+def kernel_breakdown(AF, dev, soft, label, image, nii, gpre, params, init, go, fov_mm, fov_vox, nv, V):
+    """Time every kernel of the step alone (CUDA events, mean of 5 after 2 warm-ups; operands >> L2)."""
+    from acquisition_focus_b200 import _lib as L
+    import ctypes as C
+    lib = L.lib()
+    Npix = S * S
+    nS = nv * V
+    out = {}
+    # L2 peak: device copy over a 32 MiB L2-resident buffer (same method as MEASURED_PEAKS' hbm_gbs)
+    a = torch.empty(8 * 1024 * 1024, dtype=torch.float32, device=dev); b = torch.empty_like(a)
+    t = min(_time(lambda: b.copy_(a), dev, reps=10, warm=3) for _ in range(3))
+    l2_gbs = 2 * a.numel() * 4 / (t * 1e-3) / 1e9
+    del a, b
+    # volume_min
+    t = _time(lambda: AF.volume_min(soft), dev)
+    out["volume_min(soft)"] = {"ms": t, "bytes": soft.numel() * 4, "bound": "hbm"}
+    pad_s, pad_i = AF.volume_min(soft), AF.volume_min(image)
+    spec = AF.ViewSpec(kind=L.AFFINE_PARAMS, V=V, gpre=gpre.reshape(nS, 4, 4).contiguous(), init=init, R=R, spat=S,
+                       offset_clip=OFFSET_CLIP, zoom_clip=ZOOM_CLIP, nii_affine=nii, fov_mm=tuple(fov_mm),
+                       params=params.detach().reshape(nS, NP).contiguous())
+    sd = soft.detach()
+    t = _time(lambda: AF._slice_forward_raw(sd, spec, fov_vox, L.BILINEAR, L.PAD_DEVICE, 0.0, pad_s), dev)
+    out["slice_fwd(soft C=8 bilinear)"] = {"ms": t, "bytes": nS * Npix * NUM_CLASSES * 36, "bound": "l2"}
+    t = _time(lambda: AF._slice_forward_raw(label, spec, fov_vox, L.NEAREST, L.PAD_ZERO, 0.0, None), dev)
+    out["slice_fwd(label C=8 int64 nearest)"] = {"ms": t, "bytes": nS * Npix * NUM_CLASSES * 16, "bound": "l2"}
+    t = _time(lambda: AF._slice_forward_raw(image, spec, fov_vox, L.BILINEAR, L.PAD_DEVICE, 0.0, pad_i), dev)
+    out["slice_fwd(image C=1 bilinear)"] = {"ms": t, "bytes": nS * Npix * 36, "bound": "l2"}
+    # backward pieces
+    d_vol = AF._zeros_like_strided(sd)
+    t = _time(lambda: d_vol.zero_(), dev)
+    out["memset(dVolume) [torch]"] = {"ms": t, "bytes": d_vol.numel() * 4, "bound": "hbm"}
+    ws = torch.zeros(int(lib.afb_slice_bwd_workspace_bytes(nS)), dtype=torch.uint8, device=dev)
+    d_aff = torch.zeros(nS, NP, device=dev); d_pad = torch.zeros(1, device=dev)
+    vd, vs = L.volume_desc(sd), spec.struct()
+    st = L.stream_ptr(dev)
+
+    def bwd(with_dvol):
+        L.check(lib.afb_slice_bwd(C.byref(vd), C.byref(vs), S, S, 1, L.PAD_DEVICE, 0.0, L.ptr(pad_s), L.ptr(go), None,
+                                  L.ptr(d_vol) if with_dvol else None, L.ptr(d_aff), None, L.ptr(d_pad) if with_dvol else None,
+                                  L.ptr(ws), st), "afb_slice_bwd")
+    t = _time(lambda: bwd(True), dev)
+    out["slice_bwd(soft, dVolume+dTheta)"] = {"ms": t, "bytes": nS * Npix * NUM_CLASSES * (32 + 4 + 32), "bound": "l2"}
+    t = _time(lambda: bwd(False), dev)
+    out["slice_bwd(soft, dTheta only) [not in step]"] = {"ms": t, "bytes": nS * Npix * NUM_CLASSES * (32 + 4), "bound": "l2"}
+    t = _time(lambda: L.check(lib.afb_min_grad(L.ptr(sd), L.F32, sd.numel(), L.ptr(pad_s), L.ptr(d_pad), L.ptr(d_vol), st), "afb_min_grad"), dev)
+    out["min_grad(dVolume)"] = {"ms": t, "bytes": sd.numel() * 12, "bound": "hbm"}
+    for k, v in out.items():
+        v["gbs"] = v["bytes"] / (v["ms"] * 1e-3) / 1e9
+    return out, l2_gbs
+
+
+def make_roofline(breakdown, l2_gbs):
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        hbm, src = float(json.load(open(peaks_path))["hbm_gbs"]), "of measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        hbm, src = 6650.0, "of fallback (B200_PROFILING.md 6.65 TB/s)"
+    in_step = {k: v for k, v in breakdown.items() if "not in step" not in k and "[torch]" not in k}
+    name = max(in_step, key=lambda k: in_step[k]["ms"])
+    k = in_step[name]
+    peak = hbm if k["bound"] == "hbm" else l2_gbs
+    for v in breakdown.values():
+        v["frac"] = v["gbs"] / (hbm if v["bound"] == "hbm" else l2_gbs)
+    return {"kernel": name, "bound": k["bound"], "achieved": k["gbs"], "peak": peak, "unit": "GB/s", "frac": k["gbs"] / peak,
+            "traffic": None, "peak_source": src if k["bound"] == "hbm" else "L2: device copy over a 32 MiB buffer measured in this run",
+            "algorithmic_bytes_per_launch": k["bytes"], "ms_per_launch": k["ms"]}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -228,7 +228,9 @@ def test_identity_resample_and_linearity_fullsize(afb):
     lab = cases.randint(0, 8, (1, 1, 128, 128, 128), 72).cuda()
     outl, _, _ = afb.nifti_grid_sample(lab, nii, is_label=True)
     assert torch.equal(outl, lab)
-    assert np.allclose(na.cpu().numpy(), nii.cpu().numpy(), atol=1e-9)
+    # the reference's bookkeeping moves the origin by half a voxel even for a no-op resample; keep that quirk
+    want = O.nifti_grid_sample(torch.zeros(1, 1, 128, 128, 128), nii.cpu())[2]
+    assert np.allclose(na.cpu().numpy(), want.numpy(), atol=1e-9)
     th = (torch.eye(3, 4)[None] + 0.2 * cases.randn((1, 3, 4), 73)).cuda()
     a = afb.affine_grid_sample(vol[:, :1], th, (128, 128, 1)); b = afb.affine_grid_sample(vol[:, 1:], th, (128, 128, 1))
     c = afb.affine_grid_sample(2.0 * vol[:, :1] + vol[:, 1:], th, (128, 128, 1))
