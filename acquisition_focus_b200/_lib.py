@@ -33,7 +33,7 @@ class AfbViews(C.Structure):
     _fields_ = [("kind", C.c_int), ("V", C.c_int), ("theta", C.c_void_p), ("pre", C.c_void_p),
                 ("pre_is_f64", C.c_int), ("params", C.c_void_p), ("gpre", C.c_void_p), ("init", C.c_void_p),
                 ("R", C.c_int), ("spat", C.c_int), ("offset_clip", C.c_float), ("zoom_clip", C.c_float),
-                ("nii_affine", C.c_void_p), ("fov_mm", C.c_double * 3)]
+                ("nii_affine", C.c_void_p), ("fov_mm", C.c_double * 3), ("state", C.c_void_p)]
 
 
 class AfbError(RuntimeError):
@@ -47,6 +47,13 @@ _SIGNATURES = {
     "afb_error_string": (C.c_char_p, [C.c_int]),
     "afb_volume_min_workspace_bytes": (C.c_int64, []),
     "afb_volume_min": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "afb_probe_read": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "afb_view_state_bytes": (C.c_int64, []),
+    "afb_view_prologue": (C.c_int, [C.POINTER(AfbViews), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "afb_slice_pad_grad": (C.c_int, [C.POINTER(AfbVolume), C.POINTER(AfbViews), C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
+    "afb_min_grad_fill": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "afb_slice_fwd": (C.c_int, [C.POINTER(AfbVolume), C.POINTER(AfbViews), C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),

@@ -127,6 +127,7 @@ struct ViewArgs {
     double fov_mm[3];      // D,H,W; <=0 => input FOV
     int D, H, W;           // input volume size
     int Do, Ho, Wo;        // output size
+    const void* state;     // ViewState[S] written by afb_view_prologue (NULL: compute in the sampler's own prologue)
 };
 
 // Everything the forward prologue produces; lives in shared memory.  The backward chain reads it.

@@ -96,6 +96,46 @@ min_grad_kernel(const T* __restrict__ vol, long long n, const float* __restrict_
     }
 }
 
+// d_vol = (vol == min) ? share : 0 : zero-fill and MinBackward in ONE pass (8 B/voxel instead of 4 + 12)
+template <typename T>
+__global__ void __launch_bounds__(256)
+min_grad_fill_kernel(const T* __restrict__ vol, long long n, const float* __restrict__ min_count, const float* __restrict__ d_pad,
+                     float* __restrict__ d_vol) {
+    constexpr int VEC = 16 / sizeof(T);          // elements per 16-byte load of the volume
+    const float m = __ldg(min_count), share = __ldg(d_pad) / __ldg(min_count + 1);
+    const long long nvec = n / VEC;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const uint4* __restrict__ v4 = reinterpret_cast<const uint4*>(vol);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        const uint4 raw = __ldcs(v4 + i);
+        const T* e = reinterpret_cast<const T*>(&raw);
+        float o[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) o[k] = (to_f<T>(e[k]) == m) ? share : 0.0f;
+#pragma unroll
+        for (int k = 0; k < VEC; k += 4)
+            *reinterpret_cast<float4*>(d_vol + i * VEC + k) = make_float4(o[k], o[k + 1], o[k + 2], o[k + 3]);
+    }
+    if (blockIdx.x == 0)
+        for (long long i = nvec * VEC + threadIdx.x; i < n; i += blockDim.x) d_vol[i] = (to_f<T>(vol[i]) == m) ? share : 0.0f;
+}
+
+// Measurement helper: read an (L2-resident) buffer `passes` times with 16-byte ld.global.cg loads; used by
+// bench.py to measure the L2 read-bandwidth denominator of the gather kernels' roofline on the same box.
+__global__ void __launch_bounds__(512)
+probe_read_kernel(const uint4* __restrict__ buf, long long nvec, int passes, float* __restrict__ sink) {
+    unsigned acc = 0u;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (int p = 0; p < passes; ++p) {
+#pragma unroll 4
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+            const uint4 v = __ldcg(buf + i);
+            acc += v.x ^ v.y ^ v.z ^ v.w;
+        }
+    }
+    if (acc == 0x12345678u) sink[0] = 1.0f;     // keeps the loads alive
+}
+
 __global__ void r6_fwd_kernel(const float* __restrict__ ortho, int N, float* __restrict__ mat) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
@@ -189,6 +229,21 @@ extern "C" int afb_min_grad(const void* vol, int dtype, int64_t n, const float* 
     return (int)cudaGetLastError();
 }
 
+extern "C" int afb_min_grad_fill(const void* vol, int dtype, int64_t n, const float* min_count, const float* d_pad, float* d_vol, void* stream) {
+    if (!vol || !min_count || !d_pad || !d_vol || n <= 0) return AFB_EINVAL;
+    if (((uintptr_t)vol & 15u) || ((uintptr_t)d_vol & 15u)) return AFB_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    long long want = (n / 4 + 255) / 256;
+    int blocks = (int)(want < 1 ? 1 : (want > 148 * 16 ? 148 * 16 : want));
+    switch (dtype) {
+        case AFB_F32: min_grad_fill_kernel<float><<<blocks, 256, 0, st>>>((const float*)vol, n, min_count, d_pad, d_vol); break;
+        case AFB_BF16: min_grad_fill_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)vol, n, min_count, d_pad, d_vol); break;
+        case AFB_F16: min_grad_fill_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)vol, n, min_count, d_pad, d_vol); break;
+        default: return AFB_EDTYPE;
+    }
+    return (int)cudaGetLastError();
+}
+
 extern "C" int afb_r6_fwd(const float* ortho, int N, float* mat, void* stream) {
     if (!ortho || !mat || N <= 0) return AFB_EINVAL;
     r6_fwd_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ortho, N, mat);
@@ -198,6 +253,12 @@ extern "C" int afb_r6_fwd(const float* ortho, int N, float* mat, void* stream) {
 extern "C" int afb_r6_bwd(const float* ortho, const float* grad_mat, int N, float* d_ortho, void* stream) {
     if (!ortho || !grad_mat || !d_ortho || N <= 0) return AFB_EINVAL;
     r6_bwd_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ortho, grad_mat, N, d_ortho);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int afb_probe_read(const void* buf, int64_t n_bytes, int passes, float* sink, void* stream) {
+    if (!buf || !sink || n_bytes < 16 || passes <= 0 || ((uintptr_t)buf & 15u)) return AFB_EINVAL;
+    probe_read_kernel<<<148 * 4, 512, 0, (cudaStream_t)stream>>>((const uint4*)buf, n_bytes / 16, passes, sink);
     return (int)cudaGetLastError();
 }
 

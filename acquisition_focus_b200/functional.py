@@ -18,7 +18,7 @@ plus :func:`r6_to_matrix` (``utils/transform_utils.py:27-58``) and :func:`embed_
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -77,7 +77,7 @@ class ViewSpec:
     zoom_clip: float = 0.0
     nii_affine: Optional[torch.Tensor] = None
     fov_mm: Tuple[float, float, float] = (0.0, 0.0, 0.0)
-    _keep: list = field(default_factory=list, repr=False)
+    state: Optional[torch.Tensor] = None          # output of afb_view_prologue, shared by all samplers of one acquisition
 
     def struct(self) -> L.AfbViews:
         s = L.AfbViews()
@@ -91,16 +91,19 @@ class ViewSpec:
         s.R, s.spat, s.offset_clip, s.zoom_clip = int(self.R), int(self.spat), float(self.offset_clip), float(self.zoom_clip)
         s.nii_affine = None if self.nii_affine is None else self.nii_affine.data_ptr()
         s.fov_mm = (C.c_double * 3)(*[float(v) for v in self.fov_mm])
+        s.state = None if self.state is None else self.state.data_ptr()
         return s
 
     def diff_input(self) -> torch.Tensor:
         return {L.AFFINE_GRID: self.theta, L.AFFINE_PRE: self.pre, L.AFFINE_PARAMS: self.params}[self.kind]
 
+    def replace(self, **kw) -> "ViewSpec":
+        d = dict(self.__dict__)
+        d.update(kw)
+        return ViewSpec(**d)
+
     def with_diff_input(self, t: torch.Tensor) -> "ViewSpec":
-        kw = dict(self.__dict__)
-        kw.pop("_keep")
-        kw[{L.AFFINE_GRID: "theta", L.AFFINE_PRE: "pre", L.AFFINE_PARAMS: "params"}[self.kind]] = t
-        return ViewSpec(**kw)
+        return self.replace(**{{L.AFFINE_GRID: "theta", L.AFFINE_PRE: "pre", L.AFFINE_PARAMS: "params"}[self.kind]: t})
 
 
 def _prep(t: Optional[torch.Tensor], dtype, device) -> Optional[torch.Tensor]:
@@ -109,40 +112,58 @@ def _prep(t: Optional[torch.Tensor], dtype, device) -> Optional[torch.Tensor]:
     return t.detach().to(device=device, dtype=dtype).contiguous()
 
 
-def _slice_forward_raw(volume, spec: ViewSpec, out_size, mode, pad_mode, pad_value, pad_dev, want_nii=True):
+def prepare_views(spec: ViewSpec, B: int, in_size, out_size, device):
+    """Run the view prologue ONCE for all S = B*V slices (``afb_view_prologue``): returns the spec with its
+    device-side state attached plus ``(grid_affine[B,V,4,4] fp32, nii_affine[B,V,4,4] fp64 | None, theta | None)``."""
+    lib = L.lib()
+    S = B * spec.V
+    D, H, W = (int(v) for v in in_size)
+    Do, Ho, Wo = (int(v) for v in out_size)
+    with torch.cuda.device(device):
+        state = torch.empty(S * int(lib.afb_view_state_bytes()), dtype=torch.uint8, device=device)
+        ga = torch.empty((B, spec.V, 4, 4), dtype=torch.float32, device=device)
+        nii = torch.empty((B, spec.V, 4, 4), dtype=torch.float64, device=device) if spec.kind != L.AFFINE_GRID else None
+        th = torch.empty((B, spec.V, 4, 4), dtype=torch.float32, device=device) if spec.kind == L.AFFINE_PARAMS else None
+        vs = spec.replace(state=None).struct()
+        L.check(lib.afb_view_prologue(C.byref(vs), B, D, H, W, Do, Ho, Wo, L.ptr(state), L.ptr(ga), L.ptr(nii), L.ptr(th),
+                                      L.stream_ptr(device)), "afb_view_prologue")
+    return spec.replace(state=state), ga, nii, th
+
+
+def _slice_forward_raw(volume, spec: ViewSpec, out_size, mode, pad_mode, pad_value, pad_dev):
+    """One sampler launch over all slices; ``spec.state`` must be attached (see prepare_views)."""
     lib = L.lib()
     B, Cc = volume.shape[:2]
-    S = B * spec.V
     Do, Ho, Wo = (int(v) for v in out_size)
     dev = volume.device
     with torch.cuda.device(dev):
         out = torch.empty((B, spec.V, Cc, Do, Ho, Wo), dtype=volume.dtype, device=dev)
-        ga = torch.empty((B, spec.V, 4, 4), dtype=torch.float32, device=dev)
-        nii = torch.empty((B, spec.V, 4, 4), dtype=torch.float64, device=dev) if (want_nii and spec.kind != L.AFFINE_GRID) else None
-        th = torch.empty((B, spec.V, 4, 4), dtype=torch.float32, device=dev) if spec.kind == L.AFFINE_PARAMS else None
         vd, vs = L.volume_desc(volume), spec.struct()
         L.check(lib.afb_slice_fwd(C.byref(vd), C.byref(vs), Do, Ho, Wo, mode, pad_mode, float(pad_value), L.ptr(pad_dev),
-                                  L.ptr(out), L.ptr(ga), L.ptr(nii), L.ptr(th), L.stream_ptr(dev)), "afb_slice_fwd")
-    return out, ga, nii, th
+                                  L.ptr(out), None, None, None, L.stream_ptr(dev)), "afb_slice_fwd")
+    return out
 
 
 class _SliceFn(torch.autograd.Function):
-    """out, grid_affine, nii_affine, theta = f(volume, view_input[, gpre])."""
+    """out, grid_affine, nii_affine, theta = f(volume, view_input).  ``prepared`` (optional) carries the output of
+    prepare_views so that several samplings of one acquisition share a single prologue launch."""
 
     @staticmethod
-    def forward(ctx, volume, view_input, spec: ViewSpec, out_size, mode, pad_mode, pad_value, pad_dev):
+    def forward(ctx, volume, view_input, spec: ViewSpec, out_size, mode, pad_mode, pad_value, pad_dev, prepared):
         L.require_cuda(volume, "volume")
         ctx.set_materialize_grads(False)
-        spec = spec.with_diff_input(view_input.detach().contiguous())
-        out, ga, nii, th = _slice_forward_raw(volume.detach(), spec, out_size, mode, pad_mode, pad_value, pad_dev)
+        if prepared is None:
+            spec = spec.with_diff_input(view_input.detach().contiguous())
+            prepared = prepare_views(spec, volume.shape[0], volume.shape[2:], out_size, volume.device)
+        spec, ga, nii, th = prepared
+        out = _slice_forward_raw(volume.detach(), spec, out_size, mode, pad_mode, pad_value, pad_dev)
         ctx.spec, ctx.out_size, ctx.mode = spec, tuple(int(v) for v in out_size), mode
         ctx.pad_mode, ctx.pad_value = pad_mode, pad_value
         ctx.save_for_backward(volume.detach(), pad_dev if pad_dev is not None else torch.empty(0))
         ctx.in_dtype = view_input.dtype
-        if nii is None:
-            nii = torch.empty(0, device=volume.device)
-        if th is None:
-            th = torch.empty(0, device=volume.device)
+        ga = ga.clone()          # each Function call owns its differentiable output
+        nii = nii if nii is not None else torch.empty(0, device=volume.device)
+        th = th if th is not None else torch.empty(0, device=volume.device)
         ctx.mark_non_differentiable(nii, th)
         if mode == L.NEAREST or not volume.dtype.is_floating_point:
             ctx.mark_non_differentiable(out)
@@ -157,35 +178,48 @@ class _SliceFn(torch.autograd.Function):
         dev = volume.device
         B = volume.shape[0]
         S = B * spec.V
-        need_vol = ctx.needs_input_grad[0] and volume.dtype.is_floating_point and ctx.mode == L.BILINEAR
-        need_aff = ctx.needs_input_grad[1]
+        none = (None,) * 7
         sample_grad = g_out is not None and ctx.mode == L.BILINEAR and volume.dtype.is_floating_point
+        need_vol = ctx.needs_input_grad[0] and sample_grad
+        need_aff = ctx.needs_input_grad[1]
+        if not need_vol and not need_aff:
+            return (None, None) + none
+        if not sample_grad and g_ga is None:
+            d_aff = torch.zeros(spec.diff_input().shape, dtype=ctx.in_dtype, device=dev) if need_aff else None
+            return (None, d_aff) + none
+        Do, Ho, Wo = ctx.out_size
         with torch.cuda.device(dev):
-            d_vol = _zeros_like_strided(volume) if (need_vol and sample_grad) else None
-            d_aff = torch.zeros(spec.diff_input().shape, dtype=torch.float32, device=dev) if need_aff else None
-            if not sample_grad and g_ga is None:
-                return d_vol, d_aff, None, None, None, None, None, None
-            ws = torch.zeros(int(lib.afb_slice_bwd_workspace_bytes(S)), dtype=torch.uint8, device=dev)
-            d_pad = torch.zeros(1, dtype=torch.float32, device=dev) if (d_vol is not None and ctx.pad_mode == L.PAD_DEVICE) else None
+            st = L.stream_ptr(dev)
+            vd, vs = L.volume_desc(volume), spec.struct()
             go = g_out.contiguous().float() if sample_grad else None
             gga = g_ga.contiguous().float() if g_ga is not None else None
-            vd, vs = L.volume_desc(volume), spec.struct()
-            Do, Ho, Wo = ctx.out_size
+            d_vol = None
+            if need_vol:
+                if ctx.pad_mode == L.PAD_DEVICE:
+                    # MinBackward fused with the zero fill: d_pad first (geometry + grad_out only), then
+                    # d_vol = (vol == min) ? d_pad / count : 0, then the scatter adds on top
+                    d_pad = torch.zeros(1, dtype=torch.float32, device=dev)
+                    L.check(lib.afb_slice_pad_grad(C.byref(vd), C.byref(vs), Do, Ho, Wo, L.ptr(go), L.ptr(d_pad), st),
+                            "afb_slice_pad_grad")
+                    d_vol = torch.empty_strided(volume.shape, volume.stride(), dtype=torch.float32, device=dev)
+                    L.check(lib.afb_min_grad_fill(L.ptr(volume), L.DTYPES[volume.dtype], volume.numel(), L.ptr(pad_dev),
+                                                  L.ptr(d_pad), L.ptr(d_vol), st), "afb_min_grad_fill")
+                else:
+                    d_vol = _zeros_like_strided(volume)
+            d_aff = torch.zeros(spec.diff_input().shape, dtype=torch.float32, device=dev) if need_aff else None
+            ws = torch.zeros(int(lib.afb_slice_bwd_workspace_bytes(S)), dtype=torch.uint8, device=dev)
             L.check(lib.afb_slice_bwd(C.byref(vd), C.byref(vs), Do, Ho, Wo, ctx.pad_mode, float(ctx.pad_value), L.ptr(pad_dev),
-                                      L.ptr(go), L.ptr(gga), L.ptr(d_vol), L.ptr(d_aff), None, L.ptr(d_pad), L.ptr(ws),
-                                      L.stream_ptr(dev)), "afb_slice_bwd")
-            if d_pad is not None:
-                L.check(lib.afb_min_grad(L.ptr(volume), L.DTYPES[volume.dtype], volume.numel(), L.ptr(pad_dev), L.ptr(d_pad),
-                                         L.ptr(d_vol), L.stream_ptr(dev)), "afb_min_grad")
+                                      L.ptr(go), L.ptr(gga), L.ptr(d_vol), L.ptr(d_aff), None, None, L.ptr(ws), st),
+                    "afb_slice_bwd")
         if d_aff is not None and d_aff.dtype != ctx.in_dtype:
             d_aff = d_aff.to(ctx.in_dtype)
-        return d_vol, d_aff, None, None, None, None, None, None
+        if d_vol is not None and d_vol.dtype != volume.dtype:
+            d_vol = d_vol.to(volume.dtype)
+        return (d_vol, d_aff) + none
 
 
-def _run_slice(volume, view_input, spec, out_size, mode, pad):
-    """pad: 'zero' | 'global_min' | float | device tensor [min,count]."""
-    if not _is_dense(volume):
-        volume = volume.contiguous()
+def _pad_args(volume, mode, pad):
+    """pad: 'zero' | 'global_min' | float | device tensor [min, count]."""
     pad_mode, pad_value, pad_dev = L.PAD_ZERO, 0.0, None
     if mode == L.BILINEAR:
         if isinstance(pad, torch.Tensor):
@@ -196,7 +230,14 @@ def _run_slice(volume, view_input, spec, out_size, mode, pad):
             pass
         else:
             pad_mode, pad_value = L.PAD_VALUE, float(pad)
-    return _SliceFn.apply(volume, view_input, spec, out_size, mode, pad_mode, pad_value, pad_dev)
+    return pad_mode, pad_value, pad_dev
+
+
+def _run_slice(volume, view_input, spec, out_size, mode, pad, prepared=None):
+    if not _is_dense(volume):
+        volume = volume.contiguous()
+    pad_mode, pad_value, pad_dev = _pad_args(volume, mode, pad)
+    return _SliceFn.apply(volume, view_input, spec, out_size, mode, pad_mode, pad_value, pad_dev, prepared)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -251,13 +292,15 @@ def acquire_views(x_soft_label, x_label, x_image, nifti_affine, gpre, params, in
                     zoom_clip=float(zoom_clip), nii_affine=_prep(nifti_affine, torch.float64, dev),
                     fov_mm=tuple(float(v) for v in slice_fov_mm))
     p = params.to(dev, torch.float32).reshape(B * V, NP)
-    y_soft, ga, nii, theta = _run_slice(x_soft_label, p, spec, slice_fov_vox, L.BILINEAR, soft_pad)
+    spec = spec.replace(params=p.detach().contiguous())
+    prepared = prepare_views(spec, B, x_soft_label.shape[2:], slice_fov_vox, dev)      # one prologue for everything below
+    y_soft, ga, nii, theta = _run_slice(x_soft_label, p, spec, slice_fov_vox, L.BILINEAR, soft_pad, prepared)
     y_label = y_image = None
     with torch.no_grad():
         if x_label is not None and x_label.numel() > 0:
-            y_label = _run_slice(x_label, p.detach(), spec, slice_fov_vox, L.NEAREST, "zero")[0]
+            y_label = _run_slice(x_label, p.detach(), spec, slice_fov_vox, L.NEAREST, "zero", prepared)[0]
         if x_image is not None and x_image.numel() > 0:
-            y_image = _run_slice(x_image, p.detach(), spec, slice_fov_vox, L.BILINEAR, image_pad)[0]
+            y_image = _run_slice(x_image, p.detach(), spec, slice_fov_vox, L.BILINEAR, image_pad, prepared)[0]
     return y_soft, y_label, y_image, ga, nii, theta
 
 

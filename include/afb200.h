@@ -92,11 +92,20 @@ typedef struct afb_views {
     /* PRE and PARAMS: NIfTI bookkeeping inputs */
     const double* nii_affine;   /* [B,4,4] fp64 (NULL => identity; only ratios/zooms of it are used)      */
     double fov_mm[3];           /* host: target_fov_mm in (D,H,W) order; <=0 => input FOV (nifti_utils.py:140) */
+    /* optional: per-slice view state written by afb_view_prologue ([S * afb_view_state_bytes()] bytes).
+     * NULL  => every CTA of the sampler computes the prologue itself (single-call use);
+     * !NULL => samplers read the grid affine from it (the three slicings of one acquisition and their
+     *          backward share ONE prologue) and the channels-last vector kernels become eligible. */
+    const void* state;
 } afb_views;
 
 /* ---- library info -------------------------------------------------------------------------- */
 int afb_version(void);
 const char* afb_error_string(int code);
+
+/* measurement helper (bench.py): `passes` read sweeps over buf[n_bytes] with 16-byte ld.global.cg loads in one
+ * launch; with n_bytes <= ~32 MiB the buffer is L2 resident and n_bytes*passes/time is the L2 read bandwidth. */
+int afb_probe_read(const void* buf, int64_t n_bytes, int passes, float* sink, void* stream);
 
 /* ---- min pre-pass of the bilinear path (nifti_utils.py:200) -------------------------------- */
 /* Scans n_elements of a dense tensor; writes out_min_count[0] = min as float32,
@@ -105,6 +114,16 @@ const char* afb_error_string(int code);
 int64_t afb_volume_min_workspace_bytes(void);
 int afb_volume_min(const void* data, int dtype, int64_t n_elements, float* out_min_count,
                    void* workspace, void* stream);
+
+/* ---- view prologue: raw view input -> grid affine, once per acquisition -------------------------
+ * Computes for all S = B*V slices what nifti_utils.py:36-71 and learnable_transform.py:144-230,262-289
+ * compute on the host in ~100 tiny fp32/fp64 torch ops: state (for the samplers), grid_affine_out
+ * [S,4,4] fp32, nii_affine_out [S,4,4] fp64 (PRE/PARAMS), theta_out [S,4,4] fp32 (PARAMS). Any output
+ * may be NULL.  (D,H,W) = input volume size, (Do,Ho,Wo) = output size.                              */
+int64_t afb_view_state_bytes(void);
+int afb_view_prologue(const afb_views* views, int B, int D, int H, int W, int Do, int Ho, int Wo,
+                      void* state, float* grid_affine_out, double* nii_affine_out, float* theta_out,
+                      void* stream);
 
 /* ---- slice / volume extraction, forward ------------------------------------------------------
  * out[b, v, c, i, j, k] for (i,j,k) in (Do,Ho,Wo); out dtype = volume dtype.
@@ -134,6 +153,16 @@ int afb_slice_bwd(const afb_volume* vol, const afb_views* views, int Do, int Ho,
                   const float* grad_out, const float* grad_grid_affine,
                   float* d_vol, float* d_affine, float* d_gpre, float* d_pad,
                   void* workspace, void* stream);
+
+/* d_pad += sum go * (1 - sum of in-bounds weights): the pad-value gradient alone (reads grad_out and the
+ * geometry only).  Lets the caller run MinBackward fused with the dVolume zero-fill BEFORE the scatter:
+ *   afb_slice_pad_grad -> afb_min_grad_fill -> afb_slice_bwd(d_pad = NULL).                         */
+int afb_slice_pad_grad(const afb_volume* vol, const afb_views* views, int Do, int Ho, int Wo,
+                       const float* grad_out, float* d_pad, void* stream);
+
+/* d_vol[i] = (vol[i] == min) ? d_pad / count : 0   for all i (initialises d_vol; replaces memset + afb_min_grad) */
+int afb_min_grad_fill(const void* vol, int dtype, int64_t n_elements, const float* min_count,
+                      const float* d_pad, float* d_vol, void* stream);
 
 /* MinBackward of `volume.min()` (evenly distributed over all elements equal to the min):
  * d_vol[i] += (vol[i] == min) * d_pad / count.  vol dense (any permutation), d_vol same layout. */

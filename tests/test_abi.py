@@ -29,7 +29,7 @@ def test_struct_layout_matches_header():
     from acquisition_focus_b200 import _lib
     assert C.sizeof(_lib.AfbVolume) == 8 + 4 * 6 + 8 * 5
     # afb_views: 2 int, 2 ptr, int(+pad), 3 ptr, 2 int, 2 float, ptr, 3 double
-    assert C.sizeof(_lib.AfbViews) == 8 + 16 + 8 + 24 + 8 + 8 + 8 + 24
+    assert C.sizeof(_lib.AfbViews) == 8 + 16 + 8 + 24 + 8 + 8 + 8 + 24 + 8
 
 
 def test_argument_errors_without_gpu():
