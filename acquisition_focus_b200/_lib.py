@@ -55,8 +55,7 @@ _SIGNATURES = {
                                       C.c_void_p, C.c_void_p]),
     "afb_min_grad_fill": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "afb_slice_fwd": (C.c_int, [C.POINTER(AfbVolume), C.POINTER(AfbViews), C.c_int, C.c_int, C.c_int, C.c_int,
-                                 C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                 C.c_void_p]),
+                                 C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "afb_slice_bwd_workspace_bytes": (C.c_int64, [C.c_int]),
     "afb_slice_bwd": (C.c_int, [C.POINTER(AfbVolume), C.POINTER(AfbViews), C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

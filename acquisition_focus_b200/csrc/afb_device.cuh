@@ -346,4 +346,28 @@ __device__ inline void view_prologue_warp0(const ViewArgs& va, int s, ViewState&
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// host helpers shared by the translation units
+// ------------------------------------------------------------------------------------------
+inline int make_view_args(const afb_views* views, int B, int D, int H, int W, int Do, int Ho, int Wo, bool need_state,
+                          ViewArgs& a) {
+    if (!views) return AFB_EINVAL;
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || Do <= 0 || Ho <= 0 || Wo <= 0 || views->V <= 0) return AFB_ESHAPE;
+    if ((long long)B * views->V > 65535) return AFB_ESHAPE;
+    if (views->kind < AFB_AFFINE_GRID || views->kind > AFB_AFFINE_PARAMS) return AFB_EINVAL;
+    if (need_state && !views->state) return AFB_EINVAL;
+    if (views->kind == AFB_AFFINE_PARAMS && (views->R < 0 || views->spat <= 0)) return AFB_ESHAPE;
+    a.kind = views->kind; a.V = views->V; a.theta = views->theta; a.pre = views->pre; a.pre_is_f64 = views->pre_is_f64;
+    a.params = views->params; a.gpre = views->gpre; a.init = views->init; a.R = views->R; a.spat = views->spat;
+    a.offset_clip = views->offset_clip; a.zoom_clip = views->zoom_clip; a.nii_affine = views->nii_affine;
+    for (int k = 0; k < 3; ++k) a.fov_mm[k] = views->fov_mm[k];
+    a.D = D; a.H = H; a.W = W; a.Do = Do; a.Ho = Ho; a.Wo = Wo;
+    a.state = views->state;
+    return AFB_OK;
+}
+
+// afb_views.cu: dG' (fp64 sums in ws_acc + upstream) -> gradient of the view input; re-zeroes ws_acc
+int launch_view_chain(const ViewArgs& a, int S, double* ws_acc, const float* grad_grid_affine, float* d_affine,
+                      float* d_gpre, cudaStream_t st);
+
 }  // namespace afb

@@ -140,7 +140,7 @@ def _slice_forward_raw(volume, spec: ViewSpec, out_size, mode, pad_mode, pad_val
         out = torch.empty((B, spec.V, Cc, Do, Ho, Wo), dtype=volume.dtype, device=dev)
         vd, vs = L.volume_desc(volume), spec.struct()
         L.check(lib.afb_slice_fwd(C.byref(vd), C.byref(vs), Do, Ho, Wo, mode, pad_mode, float(pad_value), L.ptr(pad_dev),
-                                  L.ptr(out), None, None, None, L.stream_ptr(dev)), "afb_slice_fwd")
+                                  L.ptr(out), L.stream_ptr(dev)), "afb_slice_fwd")
     return out
 
 

@@ -92,11 +92,11 @@ typedef struct afb_views {
     /* PRE and PARAMS: NIfTI bookkeeping inputs */
     const double* nii_affine;   /* [B,4,4] fp64 (NULL => identity; only ratios/zooms of it are used)      */
     double fov_mm[3];           /* host: target_fov_mm in (D,H,W) order; <=0 => input FOV (nifti_utils.py:140) */
-    /* optional: per-slice view state written by afb_view_prologue ([S * afb_view_state_bytes()] bytes).
-     * NULL  => every CTA of the sampler computes the prologue itself (single-call use);
-     * !NULL => samplers read the grid affine from it (the three slicings of one acquisition and their
-     *          backward share ONE prologue) and the channels-last vector kernels become eligible. */
-    const void* state;
+    /* per-slice view state, [S * afb_view_state_bytes()] bytes of caller-owned device memory: WRITTEN by
+     * afb_view_prologue, READ by afb_slice_fwd / afb_slice_bwd / afb_slice_pad_grad (required there).  The
+     * soft-label, label and image slicings of one acquisition and their backward share ONE prologue launch;
+     * keeping the fp64 4x4 algebra out of the samplers is what keeps those at <= 85 registers per thread. */
+    void* state;
 } afb_views;
 
 /* ---- library info -------------------------------------------------------------------------- */
@@ -126,13 +126,10 @@ int afb_view_prologue(const afb_views* views, int B, int D, int H, int W, int Do
                       void* stream);
 
 /* ---- slice / volume extraction, forward ------------------------------------------------------
- * out[b, v, c, i, j, k] for (i,j,k) in (Do,Ho,Wo); out dtype = volume dtype.
- * grid_affine_out [S,4,4] fp32 (G', what nifti_grid_sample returns; NULL allowed),
- * nii_affine_out  [S,4,4] fp64 (NIfTI affine of the resampled array; NULL allowed; PRE/PARAMS only),
- * theta_out       [S,4,4] fp32 (PARAMS only: theta = T@R@Z, `last_theta`; NULL allowed).          */
+ * out[b, v, c, i, j, k] for (i,j,k) in (Do,Ho,Wo); out dtype = volume dtype.  views->state must have been
+ * filled by afb_view_prologue for the same (B, V, sizes).  One launch for all S slices.             */
 int afb_slice_fwd(const afb_volume* vol, const afb_views* views, int Do, int Ho, int Wo, int mode,
-                  int pad_mode, float pad_value, const float* pad_device, void* out,
-                  float* grid_affine_out, double* nii_affine_out, float* theta_out, void* stream);
+                  int pad_mode, float pad_value, const float* pad_device, void* out, void* stream);
 
 /* ---- slice extraction, backward (bilinear only) ----------------------------------------------
  * grad_out         [S,C,Do,Ho,Wo] fp32 contiguous; NULL => chain-only (only grad_grid_affine is
@@ -146,7 +143,9 @@ int afb_slice_fwd(const afb_volume* vol, const afb_views* views, int Do, int Ho,
  * d_pad            device float accumulator (+=) of d(out)/d(pad value) = sum go*(1-sum w_inbounds),
  *                  or NULL; the caller zeroes it.  Feeds afb_min_grad (MinBackward of the reference).
  * workspace        >= afb_slice_bwd_workspace_bytes(S) bytes, ZEROED by the caller before the first
- *                  use; the kernel leaves it zeroed again on completion.                            */
+ *                  use; the call leaves it zeroed again on completion.
+ * Two launches: the sampler (re-gather, dVolume RED, CTA-reduced fp64 sums of dgrid (x) base per slice) and a
+ * one-warp-per-slice chain kernel that turns the sums + upstream gradient into d_affine / d_gpre.       */
 int64_t afb_slice_bwd_workspace_bytes(int S);
 int afb_slice_bwd(const afb_volume* vol, const afb_views* views, int Do, int Ho, int Wo,
                   int pad_mode, float pad_value, const float* pad_device,
