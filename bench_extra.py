@@ -1,0 +1,194 @@
+#!/usr/bin/env python
+"""bench_extra.py - the other BASELINE.json configurations (parity-test cases, not the headline bench line):
+
+  cfg1  single 128^3 fp32 image volume, one p2CH view, batch 1: R6 -> slice fwd+bwd (launch-latency bound)
+  cfg2  config_dict.json default: B=2 x V=3, soft label C=8 + int64 one-hot label + image, fwd+bwd
+  cfg3  slice-to-3D embedding of 6 views into the reconstruction FOV, all 6 U-Net stages, fwd+bwd
+  cfg5  256^3 volume, 256^2 slices, 16 views, C=8, fp32 and bf16 storage, fwd+bwd
+
+Each line: {"config": ..., "ms": ..., "value": ..., "unit": ..., "bytes": algorithmic bytes, "gbs": ...,
+            "torch_cuda_ms": same op through ATen's sm_100 kernels on the same GPU (the Blackwell bar)}.
+CUDA events, 3 warm-ups, mean of 10.  Run on the GPU box: python bench_extra.py > profiles/...json
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+
+def timeit(fn, reps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.mean(ts)), float(np.min(ts))
+
+
+def torch_slice(vol, theta, size, mode):
+    grid = F.affine_grid(theta, [vol.shape[0], vol.shape[1], *size], align_corners=False)
+    return F.grid_sample(vol, grid, mode=mode, padding_mode="zeros", align_corners=False)
+
+
+def cfg1(afb, dev):
+    vol = torch.randn(1, 1, 128, 128, 128, device=dev, requires_grad=True)
+    r6 = (torch.tensor([[1.0, 0, 0, 0, 1.0, 0]]) + 0.3 * torch.randn(1, 6)).to(dev).requires_grad_(True)
+    nii = torch.diag(torch.tensor([1.5, 1.5, 1.5, 1.0])).double()[None].to(dev)
+    fov_mm, fov_vox = torch.tensor([192.0, 192.0, 1.5]), torch.tensor([128, 128, 1])
+    go = torch.randn(1, 1, 128, 128, 1, device=dev)
+
+    def ours():
+        vol.grad = None; r6.grad = None
+        y, ga, _ = afb.nifti_grid_sample(vol, nii, target_fov_mm=fov_mm, target_fov_vox=fov_vox,
+                                         pre_grid_sample_affine=afb.compute_rotation_matrix_from_ortho6d(r6))
+        y.backward(go)
+
+    def ref():     # the reference's op sequence through ATen CUDA (min-shift + affine_grid + grid_sample)
+        vol.grad = None; r6.grad = None
+        from oracle import af_oracle as O
+        y, ga, _ = O.nifti_grid_sample(vol, nii, target_fov_mm=fov_mm, target_fov_vox=fov_vox,
+                                       pre_grid_sample_affine=O.r6_to_matrix(r6))
+        y.backward(go)
+    t, tmin = timeit(ours)
+    tr, _ = timeit(ref)
+    return {"config": "cfg1: 1 x 128^3 fp32, 1 view, R6 -> slice fwd+bwd (dVol + dR6)", "ms": t, "ms_min": tmin, "value": 1e3 / t,
+            "unit": "slices/s", "bytes": 104 * 128 * 128 + 2 * 8 * 2 ** 20, "torch_cuda_ms": tr,
+            "note": "launch-latency bound by construction (1.7 MB of gather traffic + 8 MiB dVolume fill + min pass)"}
+
+
+def cfg2(afb, dev):
+    from oracle import cases
+    case = cases.atm_case(128, 2, 3, seed=43)
+    soft = case["soft"].to(dev).requires_grad_(True)
+    label, image, nii = case["label"].to(dev), case["image"].to(dev), case["nii"].to(dev)
+    gpre = torch.stack(case["gpre"], 1).to(dev)
+    params = torch.stack(case["params"], 1).to(dev).requires_grad_(True)
+    init = torch.tensor([[1e-2, 0, 0, 0, 1e-2, 0, 0, 0, 0, 1.0]]).repeat(3, 1).to(dev)
+    go = torch.randn(2, 3, 8, 128, 128, 1, device=dev)
+
+    def ours():
+        soft.grad = None; params.grad = None
+        ys, yl, yi, ga, nii_o, th = afb.acquire_views(soft, label, image, nii, gpre, params, init, offset_clip=0.2, zoom_clip=0.0,
+                                                      spat=128, slice_fov_mm=[192.0, 192.0, 1.5], slice_fov_vox=[128, 128, 1])
+        ys.backward(go)
+
+    def ref():
+        from oracle import af_oracle as O
+        soft.grad = None; params.grad = None
+        loss = 0
+        for v in range(3):
+            th = O.view_theta(params[:, v], init[:1, :6], init[0, 6:9], init[:1, 9:], 0.2, 0.0, 128)
+            ys, yl, yi, ga, _ = O.atm_tail_forward(soft, label, image, nii, gpre[:, v], th, case["slice_fov_mm"], case["slice_fov_vox"])
+            loss = loss + (ys * go[:, v]).sum()
+        loss.backward()
+    t, tmin = timeit(ours)
+    tr, _ = timeit(ref, reps=3, warm=1)
+    return {"config": "cfg2: B=2 x V=3 p2CH, soft C=8 (grad) + int64 one-hot label + image, fwd+bwd wrt volume and theta",
+            "ms": t, "ms_min": tmin, "value": 6e3 / t, "unit": "slices/s", "torch_cuda_ms": tr,
+            "note": "torch_cuda_ms = oracle port of the reference's op sequence run through ATen's sm_100 CUDA kernels"}
+
+
+def cfg3(afb, dev):
+    from oracle import cases
+    out = []
+    for B in (1, 2):
+        tot_f = tot_b = tot_rf = tot_rb = 0.0
+        tot_bytes = 0
+        for c, S in ((16, 128), (32, 64), (64, 32), (128, 16), (256, 8), (256, 4)):
+            V = 6
+            case = cases.embed_case(S, c, V, B, seed=300 + S)
+            x = case["x"].to(dev).requires_grad_(True)
+            gas = [a.to(dev).requires_grad_(True) for a in case["affines"]]
+            aff = torch.stack(gas, 0)
+            go = torch.randn(B, V * c, S, S, S, device=dev)
+            sc = afb.SkipConnector(V)
+            f, _ = timeit(lambda: afb.embed_slices(x, aff, V), reps=5, warm=2)
+
+            def fb():
+                x.grad = None
+                for a in gas:
+                    a.grad = None
+                sc(x, gas).backward(go)
+            fbt, _ = timeit(fb, reps=5, warm=2)
+            from oracle import af_oracle as O
+            rf, _ = timeit(lambda: O.skip_connector(x.detach(), [a.detach() for a in gas], V), reps=2, warm=1)
+
+            def rfb():
+                x.grad = None
+                for a in gas:
+                    a.grad = None
+                O.skip_connector(x, gas, V).backward(go)
+            rfbt, _ = timeit(rfb, reps=2, warm=1)
+            nbytes = B * V * c * S ** 3 * 4 + B * V * c * S * S * 4
+            out.append({"config": f"cfg3 stage c={c} S={S} B={B} V=6", "fwd_ms": f, "fwd_bwd_ms": fbt, "bytes_fwd": nbytes,
+                        "fwd_gbs": nbytes / f / 1e6, "torch_cuda_fwd_ms": rf, "torch_cuda_fwd_bwd_ms": rfbt})
+            tot_f += f; tot_b += fbt; tot_rf += rf; tot_rb += rfbt; tot_bytes += nbytes
+            del x, gas, aff, go
+            torch.cuda.empty_cache()
+        out.append({"config": f"cfg3 all 6 stages B={B} V=6", "fwd_ms": tot_f, "fwd_bwd_ms": tot_b, "bytes_fwd": tot_bytes,
+                    "fwd_gbs": tot_bytes / tot_f / 1e6, "value": 1e3 / tot_b, "unit": "embeddings/s (fwd+bwd, 6 stages)",
+                    "torch_cuda_fwd_ms": tot_rf, "torch_cuda_fwd_bwd_ms": tot_rb})
+    return out
+
+
+def cfg5(afb, dev):
+    out = []
+    S, V, C = 256, 16, 8
+    lab = torch.randint(0, C, (1, S, S, S), device=dev)
+    soft32 = F.one_hot(lab, C).permute(0, 4, 1, 2, 3).float()
+    del lab
+    nii = torch.diag(torch.tensor([0.75, 0.75, 0.75, 1.0])).double()[None].to(dev)
+    gen = torch.Generator().manual_seed(5)
+    from acquisition_focus_b200 import synthetic as syn
+    p2 = syn.phantom_view_affines()["p2CH"]
+    gpre = torch.stack([p2 @ syn.random_aug_affine(gen, 0.3, 0.2, 0.0) for _ in range(V)])[None].to(dev)
+    R = 51
+    params = torch.cat([torch.tensor([1.0, 0, 0, 0, 1.0, 0]) + 0.3 * torch.randn(1, V, 6, generator=gen),
+                        torch.randn(1, V, 3 * R, generator=gen), torch.randn(1, V, 1, generator=gen)], -1).to(dev).requires_grad_(True)
+    init = torch.tensor([[1e-2, 0, 0, 0, 1e-2, 0, 0, 0, 0, 1.0]]).repeat(V, 1).to(dev)
+    go = torch.randn(1, V, C, S, S, 1, device=dev)
+    for dt in (torch.float32, torch.bfloat16):
+        soft = soft32.to(dt).requires_grad_(True)
+
+        def ours():
+            soft.grad = None; params.grad = None
+            ys, _, _, ga, _, _ = afb.acquire_views(soft, None, None, nii, gpre, params, init, offset_clip=0.2, zoom_clip=0.0, spat=S,
+                                                   slice_fov_mm=[192.0, 192.0, 0.75], slice_fov_vox=[S, S, 1])
+            ys.backward(go.to(dt))
+        t, tmin = timeit(ours, reps=5, warm=2)
+        e = 4 if dt == torch.float32 else 2
+        out.append({"config": f"cfg5: 1 x 8 x 256^3 {str(dt).split('.')[-1]} storage, 16 views 256^2, fwd+bwd wrt volume and theta",
+                    "ms": t, "ms_min": tmin, "value": V * 1e3 / t, "unit": "slices/s",
+                    "bytes": V * S * S * C * (8 * e + e + 8 * e + 4 + 32) + 2 * C * S ** 3 * 4})
+        del soft
+        torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    import acquisition_focus_b200 as afb
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    which = sys.argv[1:] or ["cfg1", "cfg2", "cfg3", "cfg5"]
+    for name in which:
+        res = {"cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg5": cfg5}[name](afb, dev)
+        for r in (res if isinstance(res, list) else [res]):
+            if "bytes" in r and "ms" in r:
+                r["gbs"] = r["bytes"] / r["ms"] / 1e6
+            print(json.dumps(r), flush=True)
+
+
+if __name__ == "__main__":
+    main()
