@@ -7,17 +7,28 @@
 // voxel only the corners with x index == S/2 can be non-zero, so
 //     out = wx(ix) * bilinear2D_zeros(x[b,ch], row = iz, col = iy)
 // with the identical coordinate / weight arithmetic (afb_device.cuh), i.e. bitwise the same value
-// for the same inverse affine.  The forward is a pure HBM write stream (B*V*c*S^3*4 bytes):
-// one thread = 4 consecutive w (one 16-byte streaming store per channel), coordinates computed once
-// and reused across the c channels of the view.
+// for the same inverse affine.
+//
+// forward  : pure HBM write stream (B*V*c*S^3*4 bytes).  One thread = 4 consecutive w (one 16-byte
+//            streaming store per channel).  A cheap conservative slab test (FMA, base coordinates from a
+//            shared-memory table) rejects ~97% of the voxels; only near-slab voxels run the exact
+//            bit-level coordinate code.  Coordinates are computed once and reused across the c channels.
+// backward : GATHER over the 2-D feature-map pixels, no atomics on dX (deterministic): the voxels that
+//            sample pixel (r,q) are the lattice points of A*([mid-1,mid+1) x [q-1,q+1) x [r-1,r+1)), a
+//            parallelepiped whose bounding box (<= ~5^3 candidates) is enumerated and tested with the
+//            exact forward tap code.  One thread = one pixel x one chunk of <=16 channels.  The 12 sums
+//            of d(theta) are CTA-reduced and chained through inverse() and the column normalisation by the
+//            last CTA of each (b,v).
 #include "afb_device.cuh"
 
 namespace afb {
 
 constexpr int ETHREADS = 256;
+constexpr int ECH = 16;             // channels per thread in the backward
 
-struct EmbedView {            // per (b, v), shared memory
-    float t[12];              // inverse(normalised affine)[:3,:] fp32 = affine_grid theta
+struct EmbedView {                // per (b, v), shared memory
+    float t[12];                  // inverse(normalised affine)[:3,:] fp32 = affine_grid theta
+    float fwd[12];                // normalised affine A[:3,:] (fp32 copy) for the backward's candidate boxes
     double ga[16], n[3], Ainv[16];
 };
 
@@ -33,8 +44,13 @@ __device__ inline void embed_prologue(const float* __restrict__ ga_in, EmbedView
     }
     double A[9], t[3];
     for (int r = 0; r < 3; ++r) {
-        for (int j = 0; j < 3; ++j) A[r * 3 + j] = (double)__fmul_rn(ga_in[r * 4 + j], __fdiv_rn(1.0f, nf[j]));
+        for (int j = 0; j < 3; ++j) {
+            const float a = __fmul_rn(ga_in[r * 4 + j], __fdiv_rn(1.0f, nf[j]));
+            A[r * 3 + j] = (double)a;
+            ev.fwd[r * 4 + j] = a;
+        }
         t[r] = (double)ga_in[r * 4 + 3];
+        ev.fwd[r * 4 + 3] = ga_in[r * 4 + 3];
     }
     const double c00 = A[4] * A[8] - A[5] * A[7], c01 = A[5] * A[6] - A[3] * A[8], c02 = A[3] * A[7] - A[4] * A[6];
     const double det = A[0] * c00 + A[1] * c01 + A[2] * c02;
@@ -96,8 +112,11 @@ __global__ void __launch_bounds__(ETHREADS)
 embed_fwd_kernel(const float* __restrict__ x, const float* __restrict__ affines, int B, int V, int c, int S,
                  AxisConst ax, float* __restrict__ out) {
     __shared__ EmbedView ev;
+    __shared__ float base[256];                               // base_coord table (S <= 256), else computed inline
     const int bv = blockIdx.y, b = bv / V, v = bv % V;
     if (threadIdx.x == 0) embed_prologue(affines + ((size_t)v * B + b) * 16, ev);
+    const bool use_tab = S <= 256;
+    if (use_tab) for (int i = threadIdx.x; i < S; i += ETHREADS) base[i] = base_coord(i, ax);
     __syncthreads();
     const int wv = S / VEC;                                   // vectors per row
     const long long nvec = (long long)S * S * wv;
@@ -105,26 +124,37 @@ embed_fwd_kernel(const float* __restrict__ x, const float* __restrict__ affines,
     if (e >= nvec) return;
     const int w0 = (int)(e % wv) * VEC;
     const int h = (int)((e / wv) % S), d = (int)(e / ((long long)wv * S));
-    const float by = base_coord(h, ax), bz = base_coord(d, ax);
+    const float by = use_tab ? base[h] : base_coord(h, ax), bz = use_tab ? base[d] : base_coord(d, ax);
+    const size_t S2 = (size_t)S * S, S3 = S2 * S;
+    float* __restrict__ o = out + ((size_t)b * V + v) * c * S3 + ((size_t)d * S + h) * S + w0;
+    // conservative slab test: approximate ix (contracted FMAs) of the first and last voxel of this vector;
+    // ix is affine in w, so if both ends are farther than 1.5 voxels on the same side, all VEC voxels are zero
+    const float Sf = (float)S, mid = (float)(S >> 1);
+    const float rest = ev.t[1] * by + ev.t[2] * bz + ev.t[3];
+    const float bx0 = use_tab ? base[w0] : base_coord(w0, ax), bx1 = use_tab ? base[w0 + VEC - 1] : base_coord(w0 + VEC - 1, ax);
+    const float ia = ((ev.t[0] * bx0 + rest + 1.0f) * Sf - 1.0f) * 0.5f - mid;
+    const float ib = ((ev.t[0] * bx1 + rest + 1.0f) * Sf - 1.0f) * 0.5f - mid;
+    const bool far = (ia > 1.5f && ib > 1.5f) || (ia < -1.5f && ib < -1.5f);
     Tap tp[VEC];
     unsigned any = 0u;
+    if (!far) {
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-        tp[k] = taps_of(ev.t, base_coord(w0 + k, ax), by, bz, S);
-        any |= tp[k].inb;
+        for (int k = 0; k < VEC; ++k) {
+            tp[k] = taps_of(ev.t, use_tab ? base[w0 + k] : base_coord(w0 + k, ax), by, bz, S);
+            any |= tp[k].inb;
+        }
     }
-    const size_t S2 = (size_t)S * S, S3 = S2 * S;
-    const float* __restrict__ xs = x + ((size_t)b * V + v) * c * S2;
-    float* __restrict__ o = out + ((size_t)b * V + v) * c * S3 + ((size_t)d * S + h) * S + w0;
     if (any == 0u) {
         if (VEC == 4) {
             const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
             for (int ch = 0; ch < c; ++ch) __stcs(reinterpret_cast<float4*>(o + (size_t)ch * S3), z4);
         } else {
             for (int ch = 0; ch < c; ++ch) __stcs(o + (size_t)ch * S3, 0.0f);
         }
         return;
     }
+    const float* __restrict__ xs = x + ((size_t)b * V + v) * c * S2;
     for (int ch = 0; ch < c; ++ch) {
         const float* __restrict__ xc = xs + (size_t)ch * S2;
         float r[VEC];
@@ -142,8 +172,7 @@ embed_fwd_kernel(const float* __restrict__ x, const float* __restrict__ affines,
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward: same scan; only slab voxels read grad_out; dX via RED, d(theta) block-reduced,
-// last CTA of a (b,v) chains d(theta) -> d(slicing affine) through inverse and normalisation.
+// backward
 // ------------------------------------------------------------------------------------------------
 __device__ inline void embed_chain(const EmbedView& ev, const double* __restrict__ dT /*12*/, float* __restrict__ d_ga /*16*/) {
     // d(Ainv) = [dT; 0] ; dA = -Ainv^T d(Ainv) Ainv^T
@@ -176,72 +205,100 @@ __device__ inline void embed_chain(const EmbedView& ev, const double* __restrict
     for (int r = 0; r < 4; ++r) d_ga[r * 4 + 3] = (float)dA[r * 4 + 3];
 }
 
-template <int VEC>
+// grid = (pixel tiles, channel chunks, B*V); one thread = one feature-map pixel (r,q) x <=ECH channels
 __global__ void __launch_bounds__(ETHREADS)
 embed_bwd_kernel(const float* __restrict__ go, const float* __restrict__ x, const float* __restrict__ affines,
                  int B, int V, int c, int S, AxisConst ax, float* __restrict__ d_x, float* __restrict__ d_aff,
                  double* __restrict__ ws_acc, unsigned* __restrict__ ws_counter) {
     __shared__ EmbedView ev;
+    __shared__ float base[256];
     __shared__ float red[ETHREADS / 32][12];
     __shared__ double dT[12];
     __shared__ bool is_last;
-    const int bv = blockIdx.y, b = bv / V, v = bv % V;
+    const int bv = blockIdx.z, b = bv / V, v = bv % V;
     if (threadIdx.x == 0) embed_prologue(affines + ((size_t)v * B + b) * 16, ev);
+    const bool use_tab = S <= 256;
+    if (use_tab) for (int i = threadIdx.x; i < S; i += ETHREADS) base[i] = base_coord(i, ax);
     __syncthreads();
     float part[12];
 #pragma unroll
     for (int q = 0; q < 12; ++q) part[q] = 0.0f;
-    const int wv = S / VEC;
-    const long long nvec = (long long)S * S * wv;
-    const long long e = (long long)blockIdx.x * ETHREADS + threadIdx.x;
-    if (e < nvec) {
-        const int w0 = (int)(e % wv) * VEC;
-        const int h = (int)((e / wv) % S), d = (int)(e / ((long long)wv * S));
-        const float by = base_coord(h, ax), bz = base_coord(d, ax);
-        const size_t S2 = (size_t)S * S, S3 = S2 * S;
-        const float* __restrict__ xs = x + ((size_t)b * V + v) * c * S2;
-        float* __restrict__ dxs = d_x ? d_x + ((size_t)b * V + v) * c * S2 : nullptr;
-        const float* __restrict__ g = go + ((size_t)b * V + v) * c * S3 + ((size_t)d * S + h) * S + w0;
+
+    const int pix = blockIdx.x * ETHREADS + threadIdx.x;
+    const int c0 = blockIdx.y * ECH;
+    const int nch = min(ECH, c - c0);
+    const size_t S2 = (size_t)S * S, S3 = S2 * S;
+    if (pix < S * S) {
+        const int r = pix / S, q = pix % S;                     // r: row (D index), q: column (H index)
+        const int mid = S >> 1;
+        const float Sf = (float)S;
+        // centre of the pixel's influence box in volume index space: A * normalised(mid, q, r)
+        const float pn[3] = {(2.0f * mid + 1.0f) / Sf - 1.0f, (2.0f * q + 1.0f) / Sf - 1.0f, (2.0f * r + 1.0f) / Sf - 1.0f};
+        int lo[3], hi[3];
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-            const float bx = base_coord(w0 + k, ax);
-            const Tap tp = taps_of(ev.t, bx, by, bz, S);
-            if (tp.inb == 0u) continue;
-            float dot[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int ch = 0; ch < c; ++ch) {
-                const float gv = __ldg(g + (size_t)ch * S3 + k);
+        for (int k = 0; k < 3; ++k) {
+            const float g = ev.fwd[k * 4 + 0] * pn[0] + ev.fwd[k * 4 + 1] * pn[1] + ev.fwd[k * 4 + 2] * pn[2] + ev.fwd[k * 4 + 3];
+            const float vc = ((g + 1.0f) * Sf - 1.0f) * 0.5f;
+            const float ext = fabsf(ev.fwd[k * 4 + 0]) + fabsf(ev.fwd[k * 4 + 1]) + fabsf(ev.fwd[k * 4 + 2]) + 0.05f;
+            lo[k] = max(0, (int)ceilf(vc - ext));
+            hi[k] = min(S - 1, (int)floorf(vc + ext));
+        }
+        const float* __restrict__ gbase = go + (((size_t)b * V + v) * c + c0) * S3;
+        const float* __restrict__ xp = x + (((size_t)b * V + v) * c + c0) * S2 + pix;
+        float acc[ECH], xv[ECH];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if ((tp.inb >> q) & 1u) {
-                        if (d_aff) dot[q] = fmaf(__ldg(xs + (size_t)ch * S2 + tp.off[q]), gv, dot[q]);
-                        if (dxs) atomicAdd(dxs + (size_t)ch * S2 + tp.off[q], tp.w[q] * gv);
+        for (int ch = 0; ch < ECH; ++ch) { acc[ch] = 0.0f; xv[ch] = (d_aff && ch < nch) ? __ldg(xp + (size_t)ch * S2) : 0.0f; }
+        // (lo/hi index order: k = 0 -> w (x), 1 -> h (y), 2 -> d (z))
+        for (int d = lo[2]; d <= hi[2]; ++d) {
+            const float bz = use_tab ? base[d] : base_coord(d, ax);
+            for (int h = lo[1]; h <= hi[1]; ++h) {
+                const float by = use_tab ? base[h] : base_coord(h, ax);
+                for (int w = lo[0]; w <= hi[0]; ++w) {
+                    const float bx = use_tab ? base[w] : base_coord(w, ax);
+                    const Tap tp = taps_of(ev.t, bx, by, bz, S);
+                    if (tp.inb == 0u) continue;
+                    int t = -1;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (((tp.inb >> k) & 1u) && tp.off[k] == pix) t = k;
+                    if (t < 0) continue;
+                    const float wt = tp.w[t];
+                    const float* __restrict__ gp = gbase + ((size_t)d * S + h) * S + w;
+                    float s = 0.0f;
+#pragma unroll
+                    for (int ch = 0; ch < ECH; ++ch) {
+                        if (ch < nch) {
+                            const float gv = __ldg(gp + (size_t)ch * S3);
+                            acc[ch] = fmaf(wt, gv, acc[ch]);
+                            s = fmaf(gv, xv[ch], s);
+                        }
+                    }
+                    if (d_aff) {
+                        const int dy = t & 1, dz = t >> 1;
+                        const float hs = 0.5f * Sf;
+                        const float ggx = tp.sx * s * tp.wy[dy] * tp.wz[dz] * hs;
+                        const float ggy = (dy ? s : -s) * tp.wx * tp.wz[dz] * hs;
+                        const float ggz = (dz ? s : -s) * tp.wx * tp.wy[dy] * hs;
+                        part[0] += ggx * bx; part[1] += ggx * by; part[2] += ggx * bz; part[3] += ggx;
+                        part[4] += ggy * bx; part[5] += ggy * by; part[6] += ggy * bz; part[7] += ggy;
+                        part[8] += ggz * bx; part[9] += ggz * by; part[10] += ggz * bz; part[11] += ggz;
                     }
                 }
             }
-            if (d_aff) {
-                float gix = 0.f, giy = 0.f, giz = 0.f;
+        }
+        if (d_x) {
+            float* __restrict__ dxp = d_x + (((size_t)b * V + v) * c + c0) * S2 + pix;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int dy = q & 1, dz = q >> 1;
-                    const float dq = ((tp.inb >> q) & 1u) ? dot[q] : 0.f;
-                    gix += tp.sx * dq * tp.wy[dy] * tp.wz[dz];
-                    giy += (dy ? dq : -dq) * tp.wx * tp.wz[dz];
-                    giz += (dz ? dq : -dq) * tp.wx * tp.wy[dy];
-                }
-                const float hs = 0.5f * (float)S;
-                const float ggx = gix * hs, ggy = giy * hs, ggz = giz * hs;
-                part[0] += ggx * bx; part[1] += ggx * by; part[2] += ggx * bz; part[3] += ggx;
-                part[4] += ggy * bx; part[5] += ggy * by; part[6] += ggy * bz; part[7] += ggy;
-                part[8] += ggz * bx; part[9] += ggz * by; part[10] += ggz * bz; part[11] += ggz;
-            }
+            for (int ch = 0; ch < ECH; ++ch)
+                if (ch < nch) dxp[(size_t)ch * S2] = acc[ch];
         }
     }
     if (!d_aff) return;
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
     for (int q = 0; q < 12; ++q) {
-        const float r = warp_sum(part[q]);
-        if (lane == 0) red[w][q] = r;
+        const float rr = warp_sum(part[q]);
+        if (lane == 0) red[wi][q] = rr;
     }
     __syncthreads();
     if (threadIdx.x < 12) {
@@ -252,7 +309,7 @@ embed_bwd_kernel(const float* __restrict__ go, const float* __restrict__ x, cons
     }
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) is_last = atomicAdd(ws_counter + bv, 1u) == gridDim.x - 1;
+    if (threadIdx.x == 0) is_last = atomicAdd(ws_counter + bv, 1u) == gridDim.x * gridDim.y - 1;
     __syncthreads();
     if (!is_last) return;
     __threadfence();
@@ -291,14 +348,12 @@ extern "C" int afb_embed_bwd(const float* grad_out, const float* x, const float*
     if (!grad_out || !x || !affines || !workspace) return AFB_EINVAL;
     if (!d_x && !d_affines) return AFB_EINVAL;
     if (B <= 0 || V <= 0 || c <= 0 || S <= 0 || (long long)B * V > 65535) return AFB_ESHAPE;
+    const int chunks = (c + ECH - 1) / ECH;
+    if (chunks > 65535) return AFB_ESHAPE;
     const AxisConst ax = make_axis(S);
-    cudaStream_t st = (cudaStream_t)stream;
     double* acc = (double*)workspace;
     unsigned* counter = (unsigned*)(acc + (size_t)B * V * 16);
-    const bool vec = (S % 4 == 0);
-    const long long nvec = (long long)S * S * (vec ? S / 4 : S);
-    dim3 grid((unsigned)((nvec + ETHREADS - 1) / ETHREADS), B * V);
-    if (vec) embed_bwd_kernel<4><<<grid, ETHREADS, 0, st>>>(grad_out, x, affines, B, V, c, S, ax, d_x, d_affines, acc, counter);
-    else embed_bwd_kernel<1><<<grid, ETHREADS, 0, st>>>(grad_out, x, affines, B, V, c, S, ax, d_x, d_affines, acc, counter);
+    dim3 grid((unsigned)((S * S + ETHREADS - 1) / ETHREADS), chunks, B * V);
+    embed_bwd_kernel<<<grid, ETHREADS, 0, (cudaStream_t)stream>>>(grad_out, x, affines, B, V, c, S, ax, d_x, d_affines, acc, counter);
     return (int)cudaGetLastError();
 }

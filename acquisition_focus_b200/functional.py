@@ -360,7 +360,7 @@ class _EmbedFn(torch.autograd.Function):
         if not (need_x or need_a):
             return None, None, None
         with torch.cuda.device(xd.device):
-            dx = torch.zeros_like(xd) if need_x else None
+            dx = torch.empty_like(xd) if need_x else None       # every element is written (gather, no atomics)
             da = torch.zeros_like(ad) if need_a else None
             ws = torch.zeros(int(lib.afb_embed_bwd_workspace_bytes(B * V)), dtype=torch.uint8, device=xd.device)
             L.check(lib.afb_embed_bwd(L.ptr(g.float().contiguous()), L.ptr(xd), L.ptr(ad), B, V, c, S, L.ptr(dx), L.ptr(da),

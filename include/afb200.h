@@ -177,7 +177,8 @@ int afb_r6_bwd(const float* ortho, const float* grad_mat /*[N,4,4]*/, int N, flo
  * x        [B, V*c, S, S] fp32 contiguous (view-major channels, as torch.chunk(dim=1))
  * affines  [V, B, 4, 4] fp32: the slicing grid affines (b_grid_affines stacked)
  * out      [B, V*c, S, S, S] fp32
- * Backward: d_x [B,V*c,S,S] and d_affines [V,B,4,4] (either may be NULL); d_x must be pre-zeroed.
+ * Backward: d_x [B,V*c,S,S] (fully overwritten: gather formulation, no atomics) and d_affines [V,B,4,4]
+ * (either may be NULL).
  * workspace: >= afb_embed_bwd_workspace_bytes(B*V), zeroed before first use, left zeroed.        */
 int afb_embed_fwd(const float* x, const float* affines, int B, int V, int c, int S, float* out,
                   void* stream);
