@@ -63,8 +63,9 @@ _SIGNATURES = {
     "afb_min_grad": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "afb_r6_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "afb_r6_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
-    "afb_embed_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
-    "afb_embed_bwd_workspace_bytes": (C.c_int64, [C.c_int]),
+    "afb_embed_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                 C.c_void_p]),
+    "afb_embed_workspace_bytes": (C.c_int64, [C.c_int]),
     "afb_embed_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

@@ -107,67 +107,75 @@ __device__ __forceinline__ Tap taps_of(const float* __restrict__ t, float bx, fl
 // ------------------------------------------------------------------------------------------------
 // forward: grid = (ceil(S^3/VEC / 256), B*V)
 // ------------------------------------------------------------------------------------------------
+// one thread per (b,v): the 4x4 algebra runs ONCE per call, not once per CTA (a per-CTA fp64 inverse in front of
+// the stores cost 2x in write bandwidth: 2.7 TB/s instead of >5, see profiles/embed_fwd_chunk_sweep.py)
+__global__ void embed_prologue_kernel(const float* __restrict__ affines, int B, int V, EmbedView* __restrict__ views) {
+    const int bv = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bv >= B * V) return;
+    const int b = bv / V, v = bv % V;
+    EmbedView ev;
+    embed_prologue(affines + ((size_t)v * B + b) * 16, ev);
+    views[bv] = ev;
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(ETHREADS)
-embed_fwd_kernel(const float* __restrict__ x, const float* __restrict__ affines, int B, int V, int c, int S,
+embed_fwd_kernel(const float* __restrict__ x, const EmbedView* __restrict__ views, int B, int V, int c, int S,
                  AxisConst ax, float* __restrict__ out) {
-    __shared__ EmbedView ev;
-    __shared__ float base[256];                               // base_coord table (S <= 256), else computed inline
     const int bv = blockIdx.y, b = bv / V, v = bv % V;
-    if (threadIdx.x == 0) embed_prologue(affines + ((size_t)v * B + b) * 16, ev);
-    const bool use_tab = S <= 256;
-    if (use_tab) for (int i = threadIdx.x; i < S; i += ETHREADS) base[i] = base_coord(i, ax);
-    __syncthreads();
+    float t[12];
+#pragma unroll
+    for (int q = 0; q < 12; ++q) t[q] = __ldg(views[bv].t + q);
     const int wv = S / VEC;                                   // vectors per row
     const long long nvec = (long long)S * S * wv;
-    const long long e = (long long)blockIdx.x * ETHREADS + threadIdx.x;
-    if (e >= nvec) return;
-    const int w0 = (int)(e % wv) * VEC;
-    const int h = (int)((e / wv) % S), d = (int)(e / ((long long)wv * S));
-    const float by = use_tab ? base[h] : base_coord(h, ax), bz = use_tab ? base[d] : base_coord(d, ax);
     const size_t S2 = (size_t)S * S, S3 = S2 * S;
-    float* __restrict__ o = out + ((size_t)b * V + v) * c * S3 + ((size_t)d * S + h) * S + w0;
-    // conservative slab test: approximate ix (contracted FMAs) of the first and last voxel of this vector;
-    // ix is affine in w, so if both ends are farther than 1.5 voxels on the same side, all VEC voxels are zero
     const float Sf = (float)S, mid = (float)(S >> 1);
-    const float rest = ev.t[1] * by + ev.t[2] * bz + ev.t[3];
-    const float bx0 = use_tab ? base[w0] : base_coord(w0, ax), bx1 = use_tab ? base[w0 + VEC - 1] : base_coord(w0 + VEC - 1, ax);
-    const float ia = ((ev.t[0] * bx0 + rest + 1.0f) * Sf - 1.0f) * 0.5f - mid;
-    const float ib = ((ev.t[0] * bx1 + rest + 1.0f) * Sf - 1.0f) * 0.5f - mid;
-    const bool far = (ia > 1.5f && ib > 1.5f) || (ia < -1.5f && ib < -1.5f);
-    Tap tp[VEC];
-    unsigned any = 0u;
-    if (!far) {
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-            tp[k] = taps_of(ev.t, use_tab ? base[w0 + k] : base_coord(w0 + k, ax), by, bz, S);
-            any |= tp[k].inb;
-        }
-    }
-    if (any == 0u) {
-        if (VEC == 4) {
-            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-            for (int ch = 0; ch < c; ++ch) __stcs(reinterpret_cast<float4*>(o + (size_t)ch * S3), z4);
-        } else {
-            for (int ch = 0; ch < c; ++ch) __stcs(o + (size_t)ch * S3, 0.0f);
-        }
-        return;
-    }
+    const float a1 = 2.0f / Sf, a0 = 1.0f / Sf - 1.0f;       // closed-form base coordinate (2k+1)/S-1, for the reject test only
     const float* __restrict__ xs = x + ((size_t)b * V + v) * c * S2;
-    for (int ch = 0; ch < c; ++ch) {
-        const float* __restrict__ xc = xs + (size_t)ch * S2;
-        float r[VEC];
+    for (long long e = (long long)blockIdx.x * ETHREADS + threadIdx.x; e < nvec; e += (long long)gridDim.x * ETHREADS) {
+        const int w0 = (int)(e % wv) * VEC;
+        const int h = (int)((e / wv) % S), d = (int)(e / ((long long)wv * S));
+        float* __restrict__ o = out + ((size_t)b * V + v) * c * S3 + ((size_t)d * S + h) * S + w0;
+        // conservative slab test: approximate ix of the first and last voxel of this vector; ix is affine in w, so if
+        // both ends are farther than 1.5 voxels on the same side of the plane, all VEC voxels are exactly zero
+        const float rest = t[1] * (a1 * h + a0) + t[2] * (a1 * d + a0) + t[3];
+        const float ia = ((t[0] * (a1 * w0 + a0) + rest + 1.0f) * Sf - 1.0f) * 0.5f - mid;
+        const float ib = ((t[0] * (a1 * (w0 + VEC - 1) + a0) + rest + 1.0f) * Sf - 1.0f) * 0.5f - mid;
+        const bool far = (ia > 1.5f && ib > 1.5f) || (ia < -1.5f && ib < -1.5f);
+        unsigned any = 0u;
+        Tap tp[VEC];
+        if (!far) {
+            const float by = base_coord(h, ax), bz = base_coord(d, ax);
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-            float acc = 0.0f;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if ((tp[k].inb >> q) & 1u) acc = __fadd_rn(acc, __fmul_rn(__ldg(xc + tp[k].off[q]), tp[k].w[q]));
-            r[k] = acc;
+            for (int k = 0; k < VEC; ++k) {
+                tp[k] = taps_of(t, base_coord(w0 + k, ax), by, bz, S);
+                any |= tp[k].inb;
+            }
         }
-        if (VEC == 4) __stcs(reinterpret_cast<float4*>(o + (size_t)ch * S3), make_float4(r[0], r[1], r[2], r[3]));
-        else __stcs(o + (size_t)ch * S3, r[0]);
+        if (any == 0u) {
+            if (VEC == 4) {
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+                for (int ch = 0; ch < c; ++ch) __stcs(reinterpret_cast<float4*>(o + (size_t)ch * S3), z4);
+            } else {
+                for (int ch = 0; ch < c; ++ch) __stcs(o + (size_t)ch * S3, 0.0f);
+            }
+            continue;
+        }
+        for (int ch = 0; ch < c; ++ch) {
+            const float* __restrict__ xc = xs + (size_t)ch * S2;
+            float r[VEC];
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                float acc = 0.0f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if ((tp[k].inb >> q) & 1u) acc = __fadd_rn(acc, __fmul_rn(__ldg(xc + tp[k].off[q]), tp[k].w[q]));
+                r[k] = acc;
+            }
+            if (VEC == 4) __stcs(reinterpret_cast<float4*>(o + (size_t)ch * S3), make_float4(r[0], r[1], r[2], r[3]));
+            else __stcs(o + (size_t)ch * S3, r[0]);
+        }
     }
 }
 
@@ -207,7 +215,7 @@ __device__ inline void embed_chain(const EmbedView& ev, const double* __restrict
 
 // grid = (pixel tiles, channel chunks, B*V); one thread = one feature-map pixel (r,q) x <=ECH channels
 __global__ void __launch_bounds__(ETHREADS)
-embed_bwd_kernel(const float* __restrict__ go, const float* __restrict__ x, const float* __restrict__ affines,
+embed_bwd_kernel(const float* __restrict__ go, const float* __restrict__ x, const EmbedView* __restrict__ views,
                  int B, int V, int c, int S, AxisConst ax, float* __restrict__ d_x, float* __restrict__ d_aff,
                  double* __restrict__ ws_acc, unsigned* __restrict__ ws_counter) {
     __shared__ EmbedView ev;
@@ -216,7 +224,11 @@ embed_bwd_kernel(const float* __restrict__ go, const float* __restrict__ x, cons
     __shared__ double dT[12];
     __shared__ bool is_last;
     const int bv = blockIdx.z, b = bv / V, v = bv % V;
-    if (threadIdx.x == 0) embed_prologue(affines + ((size_t)v * B + b) * 16, ev);
+    {
+        const unsigned* __restrict__ src = reinterpret_cast<const unsigned*>(views + bv);
+        unsigned* dst = reinterpret_cast<unsigned*>(&ev);
+        for (int i = threadIdx.x; i < (int)(sizeof(EmbedView) / 4); i += ETHREADS) dst[i] = __ldg(src + i);
+    }
     const bool use_tab = S <= 256;
     if (use_tab) for (int i = threadIdx.x; i < S; i += ETHREADS) base[i] = base_coord(i, ax);
     __syncthreads();
@@ -326,21 +338,33 @@ embed_bwd_kernel(const float* __restrict__ go, const float* __restrict__ x, cons
 
 using namespace afb;
 
-extern "C" int afb_embed_fwd(const float* x, const float* affines, int B, int V, int c, int S, float* out, void* stream) {
-    if (!x || !affines || !out) return AFB_EINVAL;
+extern "C" int64_t afb_embed_workspace_bytes(int n_slices) {
+    // [acc: n x 16 double][counter: n x 2 u32][EmbedView x n]
+    return (int64_t)n_slices * (16 * sizeof(double) + 2 * sizeof(unsigned) + sizeof(EmbedView));
+}
+
+static EmbedView* views_of(void* workspace, int n) {
+    return reinterpret_cast<EmbedView*>((char*)workspace + (size_t)n * (16 * sizeof(double) + 2 * sizeof(unsigned)));
+}
+
+extern "C" int afb_embed_fwd(const float* x, const float* affines, int B, int V, int c, int S, float* out, void* workspace,
+                             void* stream) {
+    if (!x || !affines || !out || !workspace) return AFB_EINVAL;
     if (B <= 0 || V <= 0 || c <= 0 || S <= 0 || (long long)B * V > 65535) return AFB_ESHAPE;
     const AxisConst ax = make_axis(S);
     cudaStream_t st = (cudaStream_t)stream;
+    EmbedView* views = views_of(workspace, B * V);
+    embed_prologue_kernel<<<(B * V + 31) / 32, 32, 0, st>>>(affines, B, V, views);
     const bool vec = (S % 4 == 0) && (((uintptr_t)out & 15u) == 0);
     const long long nvec = (long long)S * S * (vec ? S / 4 : S);
-    dim3 grid((unsigned)((nvec + ETHREADS - 1) / ETHREADS), B * V);
-    if (vec) embed_fwd_kernel<4><<<grid, ETHREADS, 0, st>>>(x, affines, B, V, c, S, ax, out);
-    else embed_fwd_kernel<1><<<grid, ETHREADS, 0, st>>>(x, affines, B, V, c, S, ax, out);
+    // grid-stride: ~8 CTAs per SM in total so that each CTA streams many rows
+    long long gx = (nvec + ETHREADS - 1) / ETHREADS;
+    const long long cap = (148 * 8 + B * V - 1) / (B * V);
+    if (gx > cap) gx = cap < 1 ? 1 : cap;
+    dim3 grid((unsigned)gx, B * V);
+    if (vec) embed_fwd_kernel<4><<<grid, ETHREADS, 0, st>>>(x, views, B, V, c, S, ax, out);
+    else embed_fwd_kernel<1><<<grid, ETHREADS, 0, st>>>(x, views, B, V, c, S, ax, out);
     return (int)cudaGetLastError();
-}
-
-extern "C" int64_t afb_embed_bwd_workspace_bytes(int n_slices) {
-    return (int64_t)n_slices * (16 * sizeof(double) + 2 * sizeof(unsigned));
 }
 
 extern "C" int afb_embed_bwd(const float* grad_out, const float* x, const float* affines, int B, int V, int c, int S,
@@ -351,9 +375,12 @@ extern "C" int afb_embed_bwd(const float* grad_out, const float* x, const float*
     const int chunks = (c + ECH - 1) / ECH;
     if (chunks > 65535) return AFB_ESHAPE;
     const AxisConst ax = make_axis(S);
+    cudaStream_t st = (cudaStream_t)stream;
     double* acc = (double*)workspace;
     unsigned* counter = (unsigned*)(acc + (size_t)B * V * 16);
+    EmbedView* views = views_of(workspace, B * V);
+    embed_prologue_kernel<<<(B * V + 31) / 32, 32, 0, st>>>(affines, B, V, views);
     dim3 grid((unsigned)((S * S + ETHREADS - 1) / ETHREADS), chunks, B * V);
-    embed_bwd_kernel<<<grid, ETHREADS, 0, (cudaStream_t)stream>>>(grad_out, x, affines, B, V, c, S, ax, d_x, d_affines, acc, counter);
+    embed_bwd_kernel<<<grid, ETHREADS, 0, st>>>(grad_out, x, views, B, V, c, S, ax, d_x, d_affines, acc, counter);
     return (int)cudaGetLastError();
 }

@@ -342,7 +342,8 @@ class _EmbedFn(torch.autograd.Function):
         c = CV // V
         out = torch.empty((B, CV, S, S, S), dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
-            L.check(L.lib().afb_embed_fwd(L.ptr(xd), L.ptr(ad), B, V, c, S, L.ptr(out), L.stream_ptr(x.device)),
+            ws = torch.empty(int(L.lib().afb_embed_workspace_bytes(B * V)), dtype=torch.uint8, device=x.device)
+            L.check(L.lib().afb_embed_fwd(L.ptr(xd), L.ptr(ad), B, V, c, S, L.ptr(out), L.ptr(ws), L.stream_ptr(x.device)),
                     "afb_embed_fwd")
         ctx.save_for_backward(xd, ad)
         ctx.V = V
@@ -362,7 +363,7 @@ class _EmbedFn(torch.autograd.Function):
         with torch.cuda.device(xd.device):
             dx = torch.empty_like(xd) if need_x else None       # every element is written (gather, no atomics)
             da = torch.zeros_like(ad) if need_a else None
-            ws = torch.zeros(int(lib.afb_embed_bwd_workspace_bytes(B * V)), dtype=torch.uint8, device=xd.device)
+            ws = torch.zeros(int(lib.afb_embed_workspace_bytes(B * V)), dtype=torch.uint8, device=xd.device)
             L.check(lib.afb_embed_bwd(L.ptr(g.float().contiguous()), L.ptr(xd), L.ptr(ad), B, V, c, S, L.ptr(dx), L.ptr(da),
                                       L.ptr(ws), L.stream_ptr(xd.device)), "afb_embed_bwd")
         return (dx.to(ctx.x_dtype) if dx is not None else None), (da.to(ctx.a_dtype) if da is not None else None), None

@@ -179,10 +179,11 @@ int afb_r6_bwd(const float* ortho, const float* grad_mat /*[N,4,4]*/, int N, flo
  * out      [B, V*c, S, S, S] fp32
  * Backward: d_x [B,V*c,S,S] (fully overwritten: gather formulation, no atomics) and d_affines [V,B,4,4]
  * (either may be NULL).
- * workspace: >= afb_embed_bwd_workspace_bytes(B*V), zeroed before first use, left zeroed.        */
+ * workspace (both calls): >= afb_embed_workspace_bytes(B*V) bytes; the first B*V*136 bytes must be zero before the
+ * first backward call and are left zeroed; the rest is scratch for the per-(b,v) inverse affines.   */
+int64_t afb_embed_workspace_bytes(int n_slices /* B*V */);
 int afb_embed_fwd(const float* x, const float* affines, int B, int V, int c, int S, float* out,
-                  void* stream);
-int64_t afb_embed_bwd_workspace_bytes(int n_slices);
+                  void* workspace, void* stream);
 int afb_embed_bwd(const float* grad_out, const float* x, const float* affines, int B, int V, int c,
                   int S, float* d_x, float* d_affines, void* workspace, void* stream);
 

@@ -36,7 +36,7 @@ def test_argument_errors_without_gpu():
     from acquisition_focus_b200 import _lib
     lib = _lib.lib()
     assert lib.afb_slice_fwd(None, None, 1, 1, 1, 0, 0, 0.0, None, None, None) == -1
-    assert lib.afb_embed_fwd(None, None, 1, 1, 1, 4, None, None) == -1
+    assert lib.afb_embed_fwd(None, None, 1, 1, 1, 4, None, None, None) == -1
     assert lib.afb_r6_fwd(None, 1, None, None) == -1
     assert lib.afb_volume_min(None, 0, 10, None, None, None) == -1
 
