@@ -19,6 +19,8 @@
 //            exact forward tap code.  One thread = one pixel x one chunk of <=16 channels.  The 12 sums
 //            of d(theta) are CTA-reduced and chained through inverse() and the column normalisation by the
 //            last CTA of each (b,v).
+#include <cstdlib>
+
 #include "afb_device.cuh"
 
 namespace afb {
@@ -29,6 +31,8 @@ constexpr int ECH = 16;             // channels per thread in the backward
 struct EmbedView {                // per (b, v), shared memory
     float t[12];                  // inverse(normalised affine)[:3,:] fp32 = affine_grid theta
     float fwd[12];                // normalised affine A[:3,:] (fp32 copy) for the backward's candidate boxes
+    int axis;                     // forward slab scan: volume axis (0=w,1=h,2=d) along which ix changes fastest
+    int K;                        // ... and the max number of slab voxels on one line along that axis
     double ga[16], n[3], Ainv[16];
 };
 
@@ -65,6 +69,11 @@ __device__ inline void embed_prologue(const float* __restrict__ ga_in, EmbedView
     }
     ev.Ainv[12] = 0.0; ev.Ainv[13] = 0.0; ev.Ainv[14] = 0.0; ev.Ainv[15] = 1.0;
     for (int i = 0; i < 12; ++i) ev.t[i] = (float)ev.Ainv[i];
+    // d ix / d (w,h,d) = t[0..2] in index units: the slab |ix - S/2| < 1 is thinnest along the largest component
+    const float m0 = fabsf(ev.t[0]), m1 = fabsf(ev.t[1]), m2 = fabsf(ev.t[2]);
+    ev.axis = (m0 >= m1 && m0 >= m2) ? 0 : (m1 >= m2 ? 1 : 2);
+    const float ma = fmaxf(fmaxf(m0, m1), fmaxf(m2, 1e-6f));
+    ev.K = (int)floorf(2.2f / ma) + 2;
 }
 
 struct Tap {                  // the (up to) 4 contributing samples of one output voxel
@@ -118,63 +127,60 @@ __global__ void embed_prologue_kernel(const float* __restrict__ affines, int B, 
     views[bv] = ev;
 }
 
-template <int VEC>
+// phase A of the forward: the output is ~97% zeros, written as one sequential stream (16-byte streaming stores)
 __global__ void __launch_bounds__(ETHREADS)
-embed_fwd_kernel(const float* __restrict__ x, const EmbedView* __restrict__ views, int B, int V, int c, int S,
-                 AxisConst ax, float* __restrict__ out) {
+embed_zero_kernel(float4* __restrict__ out4, size_t n4, float* __restrict__ out, size_t n) {
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t stride = (size_t)gridDim.x * ETHREADS;
+    for (size_t i = (size_t)blockIdx.x * ETHREADS + threadIdx.x; i < n4; i += stride) __stcs(out4 + i, z4);
+    if (blockIdx.x == 0)
+        for (size_t i = n4 * 4 + threadIdx.x; i < n; i += ETHREADS) out[i] = 0.0f;
+}
+
+// phase B: only the slab |ix - S/2| < 1 is non-zero.  It is thinnest along the volume axis with the largest
+// |d ix / d axis| (EmbedView::axis); every line along that axis crosses it in <= K voxels, found analytically and
+// then evaluated with the exact (bit-level) tap code.  One thread = one candidate voxel, all c channels
+// (channel loop unrolled so that the 4-tap gathers of several channels are in flight together).
+__global__ void __launch_bounds__(ETHREADS)
+embed_slab_kernel(const float* __restrict__ x, const EmbedView* __restrict__ views, int B, int V, int c, int S,
+                  int Kgrid, AxisConst ax, float* __restrict__ out) {
     const int bv = blockIdx.y, b = bv / V, v = bv % V;
     float t[12];
 #pragma unroll
     for (int q = 0; q < 12; ++q) t[q] = __ldg(views[bv].t + q);
-    const int wv = S / VEC;                                   // vectors per row
-    const long long nvec = (long long)S * S * wv;
-    const size_t S2 = (size_t)S * S, S3 = S2 * S;
+    const int axis = __ldg(&views[bv].axis), K = min(S, __ldg(&views[bv].K));
+    const unsigned idx = blockIdx.x * ETHREADS + threadIdx.x;
+    const unsigned line = idx / (unsigned)Kgrid;                // Kgrid candidates per line are laid out in the grid;
+    const int k0 = (int)(idx - line * (unsigned)Kgrid);         // a view that needs more (K > Kgrid) loops
+    if (line >= (unsigned)S * (unsigned)S) return;
+    const int u2 = (int)(line / (unsigned)S), u1 = (int)(line - (unsigned)u2 * (unsigned)S);
     const float Sf = (float)S, mid = (float)(S >> 1);
-    const float a1 = 2.0f / Sf, a0 = 1.0f / Sf - 1.0f;       // closed-form base coordinate (2k+1)/S-1, for the reject test only
+    const float a1 = 2.0f / Sf, a0 = 1.0f / Sf - 1.0f;       // closed-form base coordinate (2k+1)/S-1 for the line solve
+    // position p along the scan axis: ix(p) ~= ix0 + ta * p   (ta = t[axis], index units)
+    int w = 0, h = 0, d = 0;
+    if (axis == 0) { h = u1; d = u2; } else if (axis == 1) { w = u1; d = u2; } else { w = u1; h = u2; }
+    const float ta = t[axis];
+    const float g0 = t[0] * (a1 * w + a0) + t[1] * (a1 * h + a0) + t[2] * (a1 * d + a0) + t[3];
+    const float ix0 = ((g0 + 1.0f) * Sf - 1.0f) * 0.5f;
+    const float pc = (mid - ix0) / ta, half = 1.05f / fabsf(ta);
+    const int plo = (int)ceilf(pc - half);
+    const size_t S2 = (size_t)S * S, S3 = S2 * S;
     const float* __restrict__ xs = x + ((size_t)b * V + v) * c * S2;
-    for (long long e = (long long)blockIdx.x * ETHREADS + threadIdx.x; e < nvec; e += (long long)gridDim.x * ETHREADS) {
-        const int w0 = (int)(e % wv) * VEC;
-        const int h = (int)((e / wv) % S), d = (int)(e / ((long long)wv * S));
-        float* __restrict__ o = out + ((size_t)b * V + v) * c * S3 + ((size_t)d * S + h) * S + w0;
-        // conservative slab test: approximate ix of the first and last voxel of this vector; ix is affine in w, so if
-        // both ends are farther than 1.5 voxels on the same side of the plane, all VEC voxels are exactly zero
-        const float rest = t[1] * (a1 * h + a0) + t[2] * (a1 * d + a0) + t[3];
-        const float ia = ((t[0] * (a1 * w0 + a0) + rest + 1.0f) * Sf - 1.0f) * 0.5f - mid;
-        const float ib = ((t[0] * (a1 * (w0 + VEC - 1) + a0) + rest + 1.0f) * Sf - 1.0f) * 0.5f - mid;
-        const bool far = (ia > 1.5f && ib > 1.5f) || (ia < -1.5f && ib < -1.5f);
-        unsigned any = 0u;
-        Tap tp[VEC];
-        if (!far) {
-            const float by = base_coord(h, ax), bz = base_coord(d, ax);
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) {
-                tp[k] = taps_of(t, base_coord(w0 + k, ax), by, bz, S);
-                any |= tp[k].inb;
-            }
-        }
-        if (any == 0u) {
-            if (VEC == 4) {
-                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-                for (int ch = 0; ch < c; ++ch) __stcs(reinterpret_cast<float4*>(o + (size_t)ch * S3), z4);
-            } else {
-                for (int ch = 0; ch < c; ++ch) __stcs(o + (size_t)ch * S3, 0.0f);
-            }
-            continue;
-        }
+    for (int k = k0; k < K; k += Kgrid) {
+        const int p = plo + k;
+        if (p < 0 || p >= S || (float)p > pc + half) continue;
+        if (axis == 0) w = p; else if (axis == 1) h = p; else d = p;
+        const Tap tp = taps_of(t, base_coord(w, ax), base_coord(h, ax), base_coord(d, ax), S);
+        if (tp.inb == 0u) continue;
+        float* __restrict__ o = out + ((size_t)b * V + v) * c * S3 + ((size_t)d * S + h) * S + w;
+#pragma unroll 4
         for (int ch = 0; ch < c; ++ch) {
             const float* __restrict__ xc = xs + (size_t)ch * S2;
-            float r[VEC];
+            float acc = 0.0f;
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) {
-                float acc = 0.0f;
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if ((tp[k].inb >> q) & 1u) acc = __fadd_rn(acc, __fmul_rn(__ldg(xc + tp[k].off[q]), tp[k].w[q]));
-                r[k] = acc;
-            }
-            if (VEC == 4) __stcs(reinterpret_cast<float4*>(o + (size_t)ch * S3), make_float4(r[0], r[1], r[2], r[3]));
-            else __stcs(o + (size_t)ch * S3, r[0]);
+            for (int q = 0; q < 4; ++q)
+                if ((tp.inb >> q) & 1u) acc = __fadd_rn(acc, __fmul_rn(__ldg(xc + tp.off[q]), tp.w[q]));
+            o[(size_t)ch * S3] = acc;
         }
     }
 }
@@ -355,15 +361,18 @@ extern "C" int afb_embed_fwd(const float* x, const float* affines, int B, int V,
     cudaStream_t st = (cudaStream_t)stream;
     EmbedView* views = views_of(workspace, B * V);
     embed_prologue_kernel<<<(B * V + 31) / 32, 32, 0, st>>>(affines, B, V, views);
-    const bool vec = (S % 4 == 0) && (((uintptr_t)out & 15u) == 0);
-    const long long nvec = (long long)S * S * (vec ? S / 4 : S);
-    // grid-stride: ~8 CTAs per SM in total so that each CTA streams many rows
-    long long gx = (nvec + ETHREADS - 1) / ETHREADS;
-    const long long cap = (148 * 8 + B * V - 1) / (B * V);
-    if (gx > cap) gx = cap < 1 ? 1 : cap;
-    dim3 grid((unsigned)gx, B * V);
-    if (vec) embed_fwd_kernel<4><<<grid, ETHREADS, 0, st>>>(x, views, B, V, c, S, ax, out);
-    else embed_fwd_kernel<1><<<grid, ETHREADS, 0, st>>>(x, views, B, V, c, S, ax, out);
+    // phase A: zero fill (one sequential stream); phase B: the slab
+    const size_t n = (size_t)B * V * c * S * S * S;
+    const bool al = (((uintptr_t)out & 15u) == 0);
+    const size_t n4 = al ? n / 4 : 0;
+    size_t want = (n4 + ETHREADS - 1) / ETHREADS;
+    const unsigned zgrid = (unsigned)(want < 1 ? 1 : (want > 148 * 16 ? 148 * 16 : want));
+    embed_zero_kernel<<<zgrid, ETHREADS, 0, st>>>((float4*)out, n4, out, n);
+    // |t_axis| >= 0.58 for a rotation => K <= 5 slab voxels per line; views that need more loop inside the kernel
+    if ((long long)S * S * 8 >= 2147483647ll) return AFB_ESHAPE;
+    const int Kgrid = S < 6 ? S : 6;
+    dim3 grid((unsigned)(((long long)S * S * Kgrid + ETHREADS - 1) / ETHREADS), B * V);
+    embed_slab_kernel<<<grid, ETHREADS, 0, st>>>(x, views, B, V, c, S, Kgrid, ax, out);
     return (int)cudaGetLastError();
 }
 
