@@ -95,8 +95,20 @@ def cfg2(afb, dev):
         loss.backward()
     t, tmin = timeit(ours)
     tr, _ = timeit(ref, reps=3, warm=1)
+    # the same step captured once into a CUDA graph (launch-latency bound otherwise)
+    from acquisition_focus_b200.graphs import GraphedStep
+
+    def graphable():
+        soft.grad = None; params.grad = None
+        ys, yl, yi, ga, nii_o, th = afb.acquire_views(soft, label, image, nii, gpre, params, init, offset_clip=0.2, zoom_clip=0.0,
+                                                      spat=128, slice_fov_mm=[192.0, 192.0, 1.5], slice_fov_vox=[128, 128, 1])
+        ys.backward(go)
+        return ys, yl, yi, ga, soft.grad, params.grad
+    gs = GraphedStep(graphable)
+    tg, tgmin = timeit(gs)
     return {"config": "cfg2: B=2 x V=3 p2CH, soft C=8 (grad) + int64 one-hot label + image, fwd+bwd wrt volume and theta",
             "ms": t, "ms_min": tmin, "value": 6e3 / t, "unit": "slices/s", "torch_cuda_ms": tr,
+            "cuda_graph_ms": tg, "cuda_graph_ms_min": tgmin, "cuda_graph_value": 6e3 / tg,
             "note": "torch_cuda_ms = oracle port of the reference's op sequence run through ATen's sm_100 CUDA kernels"}
 
 
