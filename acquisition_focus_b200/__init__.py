@@ -10,8 +10,8 @@ Layout
   install.py       monkey-patch an importable reference checkout to run on these kernels
 """
 from . import functional  # noqa: F401
-from .functional import (acquire_views, affine_grid_sample, embed_slices, r6_to_matrix,  # noqa: F401
-                         slice_with_pre_affine, volume_min)
+from .functional import (acquire_views, acquire_views_from_labels, affine_grid_sample, embed_slices,  # noqa: F401
+                         r6_to_matrix, slice_with_pre_affine, volume_min)
 from .models.hybrid_unet import SkipConnector  # noqa: F401
 from .models.learnable_transform import AffineTransformModule, ATModulesContainer  # noqa: F401
 from .utils.nifti_utils import nifti_grid_sample  # noqa: F401

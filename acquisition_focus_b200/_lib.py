@@ -60,6 +60,10 @@ _SIGNATURES = {
     "afb_slice_bwd": (C.c_int, [C.POINTER(AfbVolume), C.POINTER(AfbViews), C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "afb_slice_onehot_fwd": (C.c_int, [C.POINTER(AfbVolume), C.c_int, C.POINTER(AfbViews), C.c_int, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "afb_slice_onehot_bwd": (C.c_int, [C.POINTER(AfbVolume), C.c_int, C.POINTER(AfbViews), C.c_int, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "afb_min_grad": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "afb_r6_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "afb_r6_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),

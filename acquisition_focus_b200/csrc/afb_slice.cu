@@ -15,110 +15,9 @@
 //              reductions (red.global.add.v4.f32) - 4x fewer L2 atomic sectors than scalar REDs.
 #include <type_traits>
 
-#include "afb_device.cuh"
+#include "afb_sampler.cuh"
 
 namespace afb {
-
-constexpr int TILE = 16;        // 16 x 16 output locations per CTA
-constexpr int NTHREADS = 256;
-
-struct VolArgs {
-    const void* data;
-    int B, C, D, H, W;
-    long long sB, sC, sD, sH, sW;
-};
-
-struct OutGeom {
-    AxisConst ax, ay, az;       // W(x), H(y), D(z) output axes
-    int Do, Ho, Wo;
-    int rows, cols;             // 2-D view of the output index space: slices (Wo==1): Do x Ho, else (Do*Ho) x Wo
-    int tiles_c;
-};
-
-struct Pix {
-    int i, j, k;                // output indices (Do, Ho, Wo)
-    bool valid;
-};
-
-__device__ __forceinline__ Pix pixel_of_thread(const OutGeom& g) {
-    const int tid = threadIdx.x;
-    const int w = tid >> 5, lane = tid & 31;
-    const int lc = ((w & 1) << 3) + (lane & 7);
-    const int lr = ((w >> 1) << 2) + (lane >> 3);
-    const int tr = blockIdx.x / g.tiles_c, tc = blockIdx.x % g.tiles_c;
-    const int row = tr * TILE + lr, col = tc * TILE + lc;
-    Pix p;
-    p.valid = row < g.rows && col < g.cols;
-    if (g.Wo == 1) {
-        p.i = row; p.j = col; p.k = 0;
-    } else {
-        p.i = row / g.Ho; p.j = row % g.Ho; p.k = col;
-    }
-    return p;
-}
-
-struct Sample {                 // un-normalised source coordinates of one output location
-    float ix, iy, iz;
-    float bx, by, bz;           // normalised base coordinates (x_k, y_j, z_i)
-};
-
-// grid affine of slice s: the first 12 floats of its ViewState (uniform address -> one broadcast per warp)
-__device__ __forceinline__ Sample sample_coords(const OutGeom& g, const Pix& p, const ViewArgs& va, int s, const VolArgs& vol) {
-    const float* __restrict__ G = reinterpret_cast<const float*>(reinterpret_cast<const ViewState*>(va.state) + s);
-    float t[12];
-#pragma unroll
-    for (int q = 0; q < 12; ++q) t[q] = __ldg(G + q);
-    Sample sm;
-    sm.bx = base_coord(p.k, g.ax);
-    sm.by = base_coord(p.j, g.ay);
-    sm.bz = base_coord(p.i, g.az);
-    sm.ix = unnormalize(grid_coord(t + 0, sm.bx, sm.by, sm.bz), (float)vol.W);
-    sm.iy = unnormalize(grid_coord(t + 4, sm.bx, sm.by, sm.bz), (float)vol.H);
-    sm.iz = unnormalize(grid_coord(t + 8, sm.bx, sm.by, sm.bz), (float)vol.D);
-    return sm;
-}
-
-// The 8 trilinear corners of one sample, kept lean (one base offset + 6 axis weights + in-bounds mask);
-// corner k = (dx,dy,dz) = (k&1, (k>>1)&1, k>>2) is ATen's order tnw,tne,tsw,tse,bnw,bne,bsw,bse.
-// Weights are formed exactly as ATen does: (wx*wy)*wz.
-struct Corners {
-    int base;                   // element offset of corner (x0,y0,z0); only dereferenced where `inb` allows
-    unsigned inb;               // bit k set <=> corner k inside the volume
-    float wx[2], wy[2], wz[2];
-    __device__ __forceinline__ float w(int k) const {
-        return __fmul_rn(__fmul_rn(wx[k & 1], wy[(k >> 1) & 1]), wz[k >> 2]);
-    }
-    __device__ __forceinline__ int off(int k, const VolArgs& vol) const {
-        return base + ((k & 1) ? (int)vol.sW : 0) + (((k >> 1) & 1) ? (int)vol.sH : 0) + ((k >> 2) ? (int)vol.sD : 0);
-    }
-    __device__ __forceinline__ bool in(int k) const { return (inb >> k) & 1u; }
-};
-
-__device__ __forceinline__ Corners corners_of(const Sample& s, const VolArgs& vol) {
-    Corners c;
-    const float x0f = floorf(s.ix), y0f = floorf(s.iy), z0f = floorf(s.iz);
-    // clamp far-out-of-field samples so that the base offset cannot overflow (all their corners are masked)
-    const int x0 = max(-2, min(__float2int_rd(s.ix), vol.W + 1));
-    const int y0 = max(-2, min(__float2int_rd(s.iy), vol.H + 1));
-    const int z0 = max(-2, min(__float2int_rd(s.iz), vol.D + 1));
-    c.wx[0] = __fsub_rn(__fadd_rn(x0f, 1.0f), s.ix); c.wx[1] = __fsub_rn(s.ix, x0f);
-    c.wy[0] = __fsub_rn(__fadd_rn(y0f, 1.0f), s.iy); c.wy[1] = __fsub_rn(s.iy, y0f);
-    c.wz[0] = __fsub_rn(__fadd_rn(z0f, 1.0f), s.iz); c.wz[1] = __fsub_rn(s.iz, z0f);
-    const bool xin[2] = {x0 >= 0 && x0 < vol.W, x0 + 1 >= 0 && x0 + 1 < vol.W};
-    const bool yin[2] = {y0 >= 0 && y0 < vol.H, y0 + 1 >= 0 && y0 + 1 < vol.H};
-    const bool zin[2] = {z0 >= 0 && z0 < vol.D, z0 + 1 >= 0 && z0 + 1 < vol.D};
-    c.inb = 0u;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) c.inb |= (xin[k & 1] && yin[(k >> 1) & 1] && zin[k >> 2]) ? (1u << k) : 0u;
-    c.base = z0 * (int)vol.sD + y0 * (int)vol.sH + x0 * (int)vol.sW;
-    return c;
-}
-
-__device__ __forceinline__ float pad_of(int pad_mode, float pad_value, const float* pad_device) {
-    if (pad_mode == AFB_PAD_DEVICE) return __ldg(pad_device);
-    if (pad_mode == AFB_PAD_VALUE) return pad_value;
-    return 0.0f;
-}
 
 // ------------------------------------------------------------------------------------------------
 // forward, generic strides (any layout, any dtype): one thread per output location, loop over C
@@ -228,48 +127,6 @@ slice_fwd_cl_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad
 // CTA reduction (shuffle -> smem) then one fp64 atomic per sum per CTA into the per-slice workspace;
 // view_chain_kernel (afb_views.cu) turns the totals into the gradient of the view input.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void grid_grad_parts(const float* dot, const Corners& cn, const Sample& sm, const VolArgs& vol,
-                                                float gsum, float* part) {
-    // d out / d (ix,iy,iz): sign pattern of ATen grid_sampler_3d_backward
-    float gix = 0.0f, giy = 0.0f, giz = 0.0f, wsum = 0.0f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int dx = k & 1, dy = (k >> 1) & 1, dz = k >> 2;
-        const float d = cn.in(k) ? dot[k] : 0.0f;
-        gix += (dx ? d : -d) * cn.wy[dy] * cn.wz[dz];
-        giy += (dy ? d : -d) * cn.wx[dx] * cn.wz[dz];
-        giz += (dz ? d : -d) * cn.wx[dx] * cn.wy[dy];
-        wsum += cn.in(k) ? cn.w(k) : 0.0f;
-    }
-    const float ggx = gix * (0.5f * (float)vol.W), ggy = giy * (0.5f * (float)vol.H), ggz = giz * (0.5f * (float)vol.D);
-    part[0] = ggx * sm.bx; part[1] = ggx * sm.by; part[2] = ggx * sm.bz; part[3] = ggx;
-    part[4] = ggy * sm.bx; part[5] = ggy * sm.by; part[6] = ggy * sm.bz; part[7] = ggy;
-    part[8] = ggz * sm.bx; part[9] = ggz * sm.by; part[10] = ggz * sm.bz; part[11] = ggz;
-    part[12] = gsum * (1.0f - wsum);
-}
-
-__device__ __forceinline__ void bwd_reduce(int s, const float* part, int pad_mode, float* __restrict__ d_pad,
-                                           double* __restrict__ ws_acc) {
-    __shared__ float red[NTHREADS / 32][13];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-    for (int q = 0; q < 13; ++q) {
-        const float r = warp_sum(part[q]);
-        if (lane == 0) red[w][q] = r;
-    }
-    __syncthreads();
-    if (threadIdx.x < 13) {
-        double t = 0.0;
-#pragma unroll
-        for (int ww = 0; ww < NTHREADS / 32; ++ww) t += (double)red[ww][threadIdx.x];
-        if (threadIdx.x < 12) {
-            atomicAdd(ws_acc + (size_t)s * 16 + threadIdx.x, t);
-        } else if (d_pad && pad_mode != AFB_PAD_ZERO) {
-            atomicAdd(d_pad, (float)t);
-        }
-    }
-}
-
 template <typename T>
 __global__ void __launch_bounds__(NTHREADS, 2)
 slice_bwd_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad_value, const float* pad_device,
@@ -392,15 +249,6 @@ slice_pad_grad_kernel(VolArgs vol, ViewArgs va, OutGeom g, const float* __restri
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static OutGeom make_geom(int Do, int Ho, int Wo) {
-    OutGeom g;
-    g.ax = make_axis(Wo); g.ay = make_axis(Ho); g.az = make_axis(Do);
-    g.Do = Do; g.Ho = Ho; g.Wo = Wo;
-    if (Wo == 1) { g.rows = Do; g.cols = Ho; } else { g.rows = Do * Ho; g.cols = Wo; }
-    g.tiles_c = (g.cols + TILE - 1) / TILE;
-    return g;
-}
-
 static int make_args(const afb_volume* vol, const afb_views* views, int Do, int Ho, int Wo, VolArgs& v, ViewArgs& a) {
     if (!vol || !vol->data) return AFB_EINVAL;
     if (vol->C <= 0) return AFB_ESHAPE;
@@ -420,8 +268,6 @@ static bool channels_last_ok(const afb_volume* vol, int n, const void* extra_ptr
     if (vol->sW % n || vol->sH % n || vol->sD % n || vol->sB % n) return false;
     return true;
 }
-
-static dim3 slice_grid(const OutGeom& g, int S) { return dim3(((g.rows + TILE - 1) / TILE) * g.tiles_c, S); }
 
 template <typename T>
 static int launch_fwd(const afb_volume* vol, const VolArgs& v, const ViewArgs& a, const OutGeom& g, int mode, int pad_mode,

@@ -304,6 +304,90 @@ def acquire_views(x_soft_label, x_label, x_image, nifti_affine, gpre, params, in
     return y_soft, y_label, y_image, ga, nii, theta
 
 
+class _OneHotSliceFn(torch.autograd.Function):
+    """y_soft, y_label, grid_affine = f(params) for an integer label map (no volume gradient exists)."""
+
+    @staticmethod
+    def forward(ctx, labels, params, spec: ViewSpec, num_classes, out_size, label_out, prepared):
+        ctx.set_materialize_grads(False)
+        spec, ga, nii, th = prepared
+        lib = L.lib()
+        dev = labels.device
+        B = labels.shape[0]
+        Do, Ho, Wo = (int(v) for v in out_size)
+        with torch.cuda.device(dev):
+            y_soft = torch.empty((B, spec.V, num_classes, Do, Ho, Wo), dtype=torch.float32, device=dev)
+            if label_out == 1:
+                y_label = torch.empty((B, spec.V, num_classes, Do, Ho, Wo), dtype=torch.int64, device=dev)
+            elif label_out == 2:
+                y_label = torch.empty((B, spec.V, Do, Ho, Wo), dtype=torch.uint8, device=dev)
+            else:
+                y_label = None
+            vd, vs = L.volume_desc(labels), spec.struct()
+            L.check(lib.afb_slice_onehot_fwd(C.byref(vd), int(num_classes), C.byref(vs), Do, Ho, Wo, L.ptr(y_soft), L.ptr(y_label),
+                                             int(label_out), L.stream_ptr(dev)), "afb_slice_onehot_fwd")
+        ctx.spec, ctx.out_size, ctx.num_classes = spec, (Do, Ho, Wo), int(num_classes)
+        ctx.save_for_backward(labels)
+        ctx.in_dtype = params.dtype
+        ga = ga.clone()
+        if y_label is None:
+            y_label = torch.empty(0, device=dev)
+        ctx.mark_non_differentiable(y_label)
+        return y_soft, y_label, ga
+
+    @staticmethod
+    def backward(ctx, g_soft, _g_label, g_ga):
+        (labels,) = ctx.saved_tensors
+        spec: ViewSpec = ctx.spec
+        if not ctx.needs_input_grad[1] or (g_soft is None and g_ga is None):
+            return (None,) * 7
+        lib = L.lib()
+        dev = labels.device
+        S = labels.shape[0] * spec.V
+        Do, Ho, Wo = ctx.out_size
+        with torch.cuda.device(dev):
+            d_aff = torch.zeros(spec.params.shape, dtype=torch.float32, device=dev)
+            ws = torch.zeros(int(lib.afb_slice_bwd_workspace_bytes(S)), dtype=torch.uint8, device=dev)
+            go = g_soft.contiguous().float() if g_soft is not None else None
+            gga = g_ga.contiguous().float() if g_ga is not None else None
+            vd, vs = L.volume_desc(labels), spec.struct()
+            L.check(lib.afb_slice_onehot_bwd(C.byref(vd), ctx.num_classes, C.byref(vs), Do, Ho, Wo, L.ptr(go), L.ptr(gga),
+                                             L.ptr(d_aff), None, L.ptr(ws), L.stream_ptr(dev)), "afb_slice_onehot_bwd")
+        return (None, d_aff.to(ctx.in_dtype), None, None, None, None, None)
+
+
+def acquire_views_from_labels(label_map, x_image, nifti_affine, gpre, params, init, *, num_classes, offset_clip, zoom_clip,
+                              spat, slice_fov_mm, slice_fov_vox, label_out="onehot", image_pad="global_min"):
+    """Same acquisition as :func:`acquire_views`, but from the INTEGER label map ``[B,D,H,W]`` (uint8/int16/int32/int64)
+    instead of its materialised fp32 / int64 one-hot volumes (``running/run_dl.py:261-264``): ``y_soft`` is bitwise what
+    :func:`acquire_views` returns for ``one_hot(label_map).float()``, ``y_label`` its nearest one-hot (``label_out=
+    'onehot'``, int64 like the reference) or the compact uint8 index slice (``'index'``) or nothing (``None``).
+    Gradients flow to ``params`` only - the reference's training case, where the volume never requires grad.
+    Returns ``(y_soft, y_label, y_image, grid_affine, nii_affine, theta)``."""
+    L.require_cuda(label_map, "label_map")
+    assert label_map.dim() == 4 and not label_map.dtype.is_floating_point
+    dev = label_map.device
+    B, V = gpre.shape[0], gpre.shape[1]
+    NP = params.shape[-1]
+    R = (NP - 7) // 3
+    lab5 = label_map[:, None]
+    if not _is_dense(lab5):
+        lab5 = lab5.contiguous()
+    p = params.to(dev, torch.float32).reshape(B * V, NP)
+    spec = ViewSpec(kind=L.AFFINE_PARAMS, V=V, gpre=_prep(gpre, torch.float32, dev).view(B * V, 4, 4),
+                    init=_prep(init, torch.float32, dev), R=R, spat=int(spat), offset_clip=float(offset_clip),
+                    zoom_clip=float(zoom_clip), nii_affine=_prep(nifti_affine, torch.float64, dev),
+                    fov_mm=tuple(float(v) for v in slice_fov_mm), params=p.detach().contiguous())
+    prepared = prepare_views(spec, B, lab5.shape[2:], slice_fov_vox, dev)
+    lo = {"onehot": 1, "index": 2, None: 0}[label_out]
+    y_soft, y_label, ga = _OneHotSliceFn.apply(lab5, p, spec, int(num_classes), slice_fov_vox, lo, prepared)
+    y_image = None
+    if x_image is not None and x_image.numel() > 0:
+        with torch.no_grad():
+            y_image = _run_slice(x_image, p.detach(), spec, slice_fov_vox, L.BILINEAR, image_pad, prepared)[0]
+    return y_soft, (y_label if lo else None), y_image, ga, prepared[2], prepared[3]
+
+
 class _R6Fn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, ortho):

@@ -366,6 +366,12 @@ def run_ours(args):
         breakdown, l2_gbs = kernel_breakdown(AF, dev, soft, label, image, nii, gpre, params, init, go, fov_mm, fov_vox, nv, V)
         roofline = make_roofline(breakdown, l2_gbs)
 
+    variants = {}
+    if not args.no_breakdown:
+        del soft, label
+        torch.cuda.empty_cache()
+        variants["training_case_from_index_labels"] = variant_from_labels(AF, dev, host_lab, host_img, nii, gpre, params, init, go,
+                                                                          fov_mm, fov_vox, nv, V)
     cpu_base = None
     if world == 1 and not args.no_cpu_baseline:
         vps = 2
@@ -382,10 +388,42 @@ def run_ours(args):
                     "steps": args.e2e_steps,
                     "what": "pinned host index-label int64 + image fp32 -> H2D -> device one-hot -> same step -> D2H reduced dTheta + grid affines"},
             "gpu_launches": LAUNCHES_PER_STEP * args.steps, "roofline": roofline, "cpu_baseline": cpu_base,
-            "kernels": breakdown, "l2_gbs_measured": l2_gbs}
+            "kernels": breakdown, "l2_gbs_measured": l2_gbs, "variants": variants}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def variant_from_labels(AF, dev, host_lab, host_img, nii, gpre, params, init, go, fov_mm, fov_vox, nv, V):
+    """The reference's TRAINING case (the volume never requires grad, only dTheta is consumed) through the one-hot-from-index
+    path: uint8 label map (2 MiB/volume) instead of the fp32 + int64 one-hot volumes (192 MiB/volume); y_soft is bitwise the
+    same.  Device-resident and end-to-end (pinned uint8 labels + fp32 image H2D, reduced dTheta + grid affines D2H)."""
+    from acquisition_focus_b200 import parallel as par
+    host_u8 = host_lab.to(torch.uint8).pin_memory()
+    lab = host_u8.to(dev)
+    image = host_img.to(dev)
+    g_host = torch.empty((V, NP), dtype=torch.float32).pin_memory()
+    ga_host = torch.empty((nv, V, 4, 4), dtype=torch.float32).pin_memory()
+
+    def step(lab_t, img_t):
+        params.grad = None
+        ys, yl, yi, ga, nii_o, th = AF.acquire_views_from_labels(lab_t, img_t, nii, gpre, params, init, num_classes=NUM_CLASSES,
+                                                                 offset_clip=OFFSET_CLIP, zoom_clip=ZOOM_CLIP, spat=S,
+                                                                 slice_fov_mm=fov_mm, slice_fov_vox=fov_vox)
+        torch.autograd.backward([ys], [go])
+        return par.reduce_view_grads(params.grad), ga
+
+    def e2e():
+        g, ga = step(host_u8.to(dev, non_blocking=True), host_img.to(dev, non_blocking=True))
+        g_host.copy_(g, non_blocking=True); ga_host.copy_(ga.detach(), non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+    t = _time(lambda: step(lab, image), dev, reps=10, warm=3)
+    te = _time(e2e, dev, reps=3, warm=1)
+    return {"ms_per_step": t, "value": nv * V / (t * 1e-3), "unit": UNIT,
+            "e2e": {"value": nv * V / (te * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(host_u8.numel() + host_img.numel() * 4), "d2h_bytes_per_step": int(g_host.numel() * 4 + ga_host.numel() * 4)},
+            "what": "uint8 index labels -> y_soft (C=8, bitwise = dense path) + int64 one-hot nearest label + image slices, backward w.r.t. "
+                    "the view parameters only (no dVolume): view_prologue, volume_min(image), onehot_fwd, slice_fwd(image), onehot_bwd, view_chain"}
 
 
 def _time(fn, dev, reps=5, warm=2):

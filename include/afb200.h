@@ -163,6 +163,22 @@ int afb_slice_pad_grad(const afb_volume* vol, const afb_views* views, int Do, in
 int afb_min_grad_fill(const void* vol, int dtype, int64_t n_elements, const float* min_count,
                       const float* d_pad, float* d_vol, void* stream);
 
+/* ---- one-hot label slicing straight from the integer label map (running/run_dl.py:261-264 + the two label
+ * slicings of learnable_transform.py:287-298, without materialising the fp32 / int64 one-hot volumes) ----------
+ * labels      [B,1,D,H,W] integer index map (AFB_U8 / I16 / I32 / I64), C field = 1, any strides
+ * num_classes <= 16
+ * y_soft      [S,num_classes,Do,Ho,Wo] fp32 = bilinear slice of one_hot(labels).float(), bitwise what afb_slice_fwd
+ *             gives on the materialised volume (pad = min = 0); NULL to skip
+ * y_label     label_out 1: [S,num_classes,Do,Ho,Wo] int64 = nearest slice of the int64 one-hot;
+ *             label_out 2: [S,Do,Ho,Wo] uint8 nearest label index (0 out of field); label_out 0: none
+ * Backward: gradient w.r.t. the view input only (an integer volume has none): the reference's training case.
+ * workspace as for afb_slice_bwd.                                                                       */
+int afb_slice_onehot_fwd(const afb_volume* labels, int num_classes, const afb_views* views, int Do, int Ho,
+                         int Wo, float* y_soft, void* y_label, int label_out, void* stream);
+int afb_slice_onehot_bwd(const afb_volume* labels, int num_classes, const afb_views* views, int Do, int Ho,
+                         int Wo, const float* grad_y_soft, const float* grad_grid_affine, float* d_affine,
+                         float* d_gpre, void* workspace, void* stream);
+
 /* MinBackward of `volume.min()` (evenly distributed over all elements equal to the min):
  * d_vol[i] += (vol[i] == min) * d_pad / count.  vol dense (any permutation), d_vol same layout. */
 int afb_min_grad(const void* vol, int dtype, int64_t n_elements, const float* min_count,
