@@ -47,17 +47,29 @@ def _zeros_like_strided(t: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
     return out.zero_()
 
 
-def volume_min(volume: torch.Tensor) -> torch.Tensor:
-    """``volume.min()`` of nifti_utils.py:200 as a device tensor ``[min, multiplicity]`` (fp32)."""
+def volume_min(volume: torch.Tensor, with_mask: bool = False) -> torch.Tensor:
+    """``volume.min()`` of nifti_utils.py:200 as a device tensor ``[min, multiplicity]`` (fp32).
+
+    ``with_mask`` (fp32 volumes): the same pass also leaves a 1-bit-per-voxel record of where the minimum sits
+    (``afb_volume_min_mask``), attached to the result as ``._afb_mask``; the backward then rebuilds MinBackward
+    without re-reading the volume (half the HBM traffic of the dVolume fill).  The record refers to the memory
+    layout of ``volume`` at call time."""
     L.require_cuda(volume, "volume")
     if not _is_dense(volume):
         volume = volume.contiguous()
     lib = L.lib()
-    with torch.cuda.device(volume.device):
-        ws = torch.empty(int(lib.afb_volume_min_workspace_bytes()), dtype=torch.uint8, device=volume.device)
-        out = torch.empty(2, dtype=torch.float32, device=volume.device)
-        L.check(lib.afb_volume_min(L.ptr(volume), L.DTYPES[volume.dtype], volume.numel(), L.ptr(out), L.ptr(ws),
-                                   L.stream_ptr(volume.device)), "afb_volume_min")
+    dev = volume.device
+    with torch.cuda.device(dev):
+        ws = torch.empty(int(lib.afb_volume_min_workspace_bytes()), dtype=torch.uint8, device=dev)
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        if with_mask and volume.dtype == torch.float32:
+            mask = torch.empty(int(lib.afb_min_mask_bytes(volume.numel())), dtype=torch.uint8, device=dev)
+            L.check(lib.afb_volume_min_mask(L.ptr(volume), volume.numel(), L.ptr(out), L.ptr(mask), L.ptr(ws),
+                                            L.stream_ptr(dev)), "afb_volume_min_mask")
+            out._afb_mask = mask
+        else:
+            L.check(lib.afb_volume_min(L.ptr(volume), L.DTYPES[volume.dtype], volume.numel(), L.ptr(out), L.ptr(ws),
+                                       L.stream_ptr(dev)), "afb_volume_min")
     return out
 
 
@@ -160,6 +172,7 @@ class _SliceFn(torch.autograd.Function):
         ctx.spec, ctx.out_size, ctx.mode = spec, tuple(int(v) for v in out_size), mode
         ctx.pad_mode, ctx.pad_value = pad_mode, pad_value
         ctx.save_for_backward(volume.detach(), pad_dev if pad_dev is not None else torch.empty(0))
+        ctx.pad_mask = getattr(pad_dev, "_afb_mask", None) if pad_dev is not None else None
         ctx.in_dtype = view_input.dtype
         ga = ga.clone()          # each Function call owns its differentiable output
         nii = nii if nii is not None else torch.empty(0, device=volume.device)
@@ -202,8 +215,12 @@ class _SliceFn(torch.autograd.Function):
                     L.check(lib.afb_slice_pad_grad(C.byref(vd), C.byref(vs), Do, Ho, Wo, L.ptr(go), L.ptr(d_pad), st),
                             "afb_slice_pad_grad")
                     d_vol = torch.empty_strided(volume.shape, volume.stride(), dtype=torch.float32, device=dev)
-                    L.check(lib.afb_min_grad_fill(L.ptr(volume), L.DTYPES[volume.dtype], volume.numel(), L.ptr(pad_dev),
-                                                  L.ptr(d_pad), L.ptr(d_vol), st), "afb_min_grad_fill")
+                    if ctx.pad_mask is not None:        # 1-bit record left by the forward's min pass: no volume re-read
+                        L.check(lib.afb_min_grad_fill_mask(L.ptr(ctx.pad_mask), volume.numel(), L.ptr(pad_dev), L.ptr(d_pad),
+                                                           L.ptr(d_vol), st), "afb_min_grad_fill_mask")
+                    else:
+                        L.check(lib.afb_min_grad_fill(L.ptr(volume), L.DTYPES[volume.dtype], volume.numel(), L.ptr(pad_dev),
+                                                      L.ptr(d_pad), L.ptr(d_vol), st), "afb_min_grad_fill")
                 else:
                     d_vol = _zeros_like_strided(volume)
             d_aff = torch.zeros(spec.diff_input().shape, dtype=torch.float32, device=dev) if need_aff else None
@@ -225,7 +242,8 @@ def _pad_args(volume, mode, pad):
         if isinstance(pad, torch.Tensor):
             pad_mode, pad_dev = L.PAD_DEVICE, pad
         elif pad == "global_min":
-            pad_mode, pad_dev = L.PAD_DEVICE, volume_min(volume)
+            want_dvol = volume.requires_grad and torch.is_grad_enabled()
+            pad_mode, pad_dev = L.PAD_DEVICE, volume_min(volume, with_mask=want_dvol)
         elif pad == "zero":
             pass
         else:
@@ -386,6 +404,31 @@ def acquire_views_from_labels(label_map, x_image, nifti_affine, gpre, params, in
         with torch.no_grad():
             y_image = _run_slice(x_image, p.detach(), spec, slice_fov_vox, L.BILINEAR, image_pad, prepared)[0]
     return y_soft, (y_label if lo else None), y_image, ga, prepared[2], prepared[3]
+
+
+def onehot_resample_with_pre_affine(label_map, nii_affine, pre_affine, fov_mm, fov_vox, num_classes):
+    """``nifti_grid_sample(one_hot(label_map).float(), ..., is_label=False)`` without materialising the one-hot input
+    (e.g. the pre-oriented prescan volume fed to the LocalizationNet, ``models/learnable_transform.py:248-255``).
+    label_map ``[B,D,H,W]`` integer -> ``[B,num_classes,Do,Ho,Wo]`` fp32; no gradient (the reference calls it under no_grad)."""
+    L.require_cuda(label_map, "label_map")
+    dev = label_map.device
+    B = label_map.shape[0]
+    lab5 = label_map[:, None]
+    if not _is_dense(lab5):
+        lab5 = lab5.contiguous()
+    pre = pre_affine.detach().to(dev)
+    if pre.dtype not in (torch.float32, torch.float64):
+        pre = pre.float()
+    spec = ViewSpec(kind=L.AFFINE_PRE, V=1, nii_affine=_prep(nii_affine, torch.float64, dev), fov_mm=tuple(float(v) for v in fov_mm),
+                    pre=pre.contiguous())
+    prepared = prepare_views(spec, B, lab5.shape[2:], fov_vox, dev)
+    Do, Ho, Wo = (int(v) for v in fov_vox)
+    with torch.cuda.device(dev):
+        out = torch.empty((B, 1, int(num_classes), Do, Ho, Wo), dtype=torch.float32, device=dev)
+        vd, vs = L.volume_desc(lab5), prepared[0].struct()
+        L.check(L.lib().afb_slice_onehot_fwd(C.byref(vd), int(num_classes), C.byref(vs), Do, Ho, Wo, L.ptr(out), None, 0,
+                                             L.stream_ptr(dev)), "afb_slice_onehot_fwd")
+    return out[:, 0], prepared[1][:, 0], prepared[2][:, 0]
 
 
 class _R6Fn(torch.autograd.Function):

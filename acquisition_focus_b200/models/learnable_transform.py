@@ -124,6 +124,13 @@ class AffineTransformModule(nn.Module):
                                             pre_grid_sample_affine=grid_affine_pre_mlp)
         return self.localization_net(x_pre)
 
+    def mlp_head_from_labels(self, label_map, num_classes, nifti_affine, grid_affine_pre_mlp):
+        """Same as :meth:`mlp_head` but from the integer label map ``[B,D,H,W]`` (no one-hot volume is materialised)."""
+        with torch.no_grad():
+            x_pre, _, _ = AF.onehot_resample_with_pre_affine(label_map, nifti_affine, grid_affine_pre_mlp,
+                                                             self.volume_fov_mm.tolist(), self.volume_fov_vox.tolist(), num_classes)
+        return self.localization_net(x_pre)
+
     def forward(self, x_soft_label, x_label, x_image, nifti_affine, grid_affine_pre_mlp, theta_override=None):
         soft_none = x_soft_label is None or x_soft_label.numel() == 0
         assert not soft_none
@@ -209,6 +216,27 @@ class ATModulesContainer(nn.ModuleList):
             x_soft_label, x_label, x_image, nifti_affine, gpre, params, init, offset_clip=a0.offset_clip_value,
             zoom_clip=a0.zoom_clip_value, spat=a0.spat, slice_fov_mm=a0.slice_fov_mm.tolist(),
             slice_fov_vox=a0.slice_fov_vox.tolist())
+        for v, m in enumerate(atms):
+            m.last_theta, m.last_grid_affine, m.last_transformed_nifti_affine = theta[:, v], ga[:, v], nii[:, v]
+        return y_soft, y_label, y_image, ga, nii
+
+    def acquire_from_labels(self, label_map, num_classes, x_image, nifti_affine, view_pre_affines, mlp_outs: Optional[list] = None,
+                            modules: Optional[list] = None, label_out="onehot"):
+        """:meth:`acquire` from the INTEGER label map ``[B,D,H,W]``: neither ``one_hot(label).float()`` nor the int64
+        one-hot volume is materialised (``running/run_dl.py:261-264``); gradients flow to the view parameters only, which is
+        all the reference's training step consumes.  ``modules``: the active view modules (default: all)."""
+        atms = list(self) if modules is None else list(modules)
+        dev = label_map.device
+        gpre = torch.stack([g.to(dev, torch.float32) for g in view_pre_affines], dim=1)
+        if mlp_outs is None:
+            mlp_outs = [m.mlp_head_from_labels(label_map, num_classes, nifti_affine, g) for m, g in zip(atms, view_pre_affines)]
+        params = torch.stack(mlp_outs, dim=1)
+        init = torch.stack([m.init_vector() for m in atms]).to(dev)
+        a0 = atms[0]
+        y_soft, y_label, y_image, ga, nii, theta = AF.acquire_views_from_labels(
+            label_map, x_image, nifti_affine, gpre, params, init, num_classes=num_classes, offset_clip=a0.offset_clip_value,
+            zoom_clip=a0.zoom_clip_value, spat=a0.spat, slice_fov_mm=a0.slice_fov_mm.tolist(),
+            slice_fov_vox=a0.slice_fov_vox.tolist(), label_out=label_out)
         for v, m in enumerate(atms):
             m.last_theta, m.last_grid_affine, m.last_transformed_nifti_affine = theta[:, v], ga[:, v], nii[:, v]
         return y_soft, y_label, y_image, ga, nii

@@ -1,0 +1,91 @@
+"""Mirror of the reference's per-batch caller of the hot path, ``running/run_dl.py:208-329``
+(``apply_affine_augmentation``, ``get_input_affine_for_atm``, ``get_reconstruction_model_input``), on top of the
+fused kernels: what the reference does with 14 ``nifti_grid_sample`` calls and ~10^4 ATen launches per batch
+(B=2, V=3) becomes 2 hires resamples + ONE acquisition over all B x V slices straight from the integer label map.
+
+Same signature and return tuple as the reference: ``(b_input[B, V*C, H, W], b_target[B, C, D, H, W] long,
+grid_affines: list[V] of [B,4,4])``; ``config`` is any object with the reference's attribute names
+(``config_dict.json``).  Only ``label_slice_type == 'from-gt'`` is on this path (``'from-segmented'`` needs the
+nnU-Net segmenter, out of scope).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from ..synthetic import random_aug_affine
+from ..utils.nifti_utils import nifti_grid_sample
+
+
+def apply_affine_augmentation(affine_list, zoom_strength=0.1, offset_strength=0.1, rotation_strength=0.1, generator=None):
+    """run_dl.py:208-223: right-multiply every affine of the list by ONE random affine per batch element (host RNG)."""
+    gen = generator if generator is not None else torch.Generator().manual_seed(int(torch.randint(0, 2 ** 31 - 1, (1,))))
+    B = affine_list[0].shape[0]
+    b_affine = torch.stack([random_aug_affine(gen, rotation_strength, zoom_strength, offset_strength) for _ in range(B)])
+    return [a @ b_affine.to(a) for a in affine_list]
+
+
+def get_input_affine_for_atm(atm, base_affine, b_view_affines):
+    """run_dl.py:227-234: ``Gpre = base_affine^-1 @ view_affine[view_id]`` (or the module's random affine for 'RND')."""
+    B = base_affine.shape[0]
+    if atm.view_id == "RND":
+        return atm.random_grid_affine.repeat(B, 1, 1).to(base_affine)
+    return base_affine.inverse() @ torch.as_tensor(b_view_affines[atm.view_id]).view(B, 4, 4).to(base_affine)
+
+
+def get_reconstruction_model_input(batch, phase, config, num_classes, atm_container, segment_fn=None, generator=None):
+    """run_dl.py:238-329.  ``batch``: {'label' [B,D,H,W] int, 'image' [B,D,H,W] float, 'additional_data': {'nifti_affine'
+    [B,4,4], 'gt_view_affines' | 'prescan_view_affines': {view name: [B,4,4], 'centroids': [B,4,4]}}}, CUDA tensors."""
+    if getattr(config, "label_slice_type", "from-gt") != "from-gt":
+        raise NotImplementedError("only label_slice_type='from-gt' is on the accelerated path")
+    b_label, b_image = batch["label"], batch["image"]
+    key = "gt_view_affines" if config.clinical_view_affine_type == "from-gt" else "prescan_view_affines"
+    b_view_affines = batch["additional_data"][key]
+    nifti_affine = batch["additional_data"]["nifti_affine"]
+    base_affine = torch.as_tensor(b_view_affines["centroids"]).to(nifti_affine)
+
+    with torch.no_grad():                                                              # :251-259
+        hires_mm, hires_vox = torch.as_tensor(config.hires_fov_mm), torch.as_tensor(config.hires_fov_vox)
+        b_label, _, nifti_affine = nifti_grid_sample(b_label.unsqueeze(1), nifti_affine, target_fov_mm=hires_mm,
+                                                     target_fov_vox=hires_vox, is_label=True, pre_grid_sample_affine=base_affine)
+        b_image, _, _ = nifti_grid_sample(b_image.unsqueeze(1), nifti_affine, target_fov_mm=hires_mm, target_fov_vox=hires_vox,
+                                          is_label=False, pre_grid_sample_affine=base_affine)
+        b_label = b_label.squeeze(1)                                                   # [B,D,H,W] integer, stays an index map
+    B, D, H, W = b_label.shape
+
+    for atm in atm_container:
+        atm.use_affine_theta = config.use_affine_theta
+    active = list(atm_container.get_active_view_modules())                            # :269-271
+    input_grid_affines = [get_input_affine_for_atm(m, base_affine, b_view_affines).to(torch.float32) for m in active]
+    if config.do_augment_input_orientation and phase in config.aug_phases:            # :273-278
+        s = config.sample_augment_strength
+        input_grid_affines = apply_affine_augmentation(input_grid_affines, rotation_strength=0.1 * s, zoom_strength=0.2 * s,
+                                                       offset_strength=0.0, generator=generator)
+
+    # per-view MLP heads; gradient context per view as in :283-289
+    mlp_outs = []
+    for i, (m, ga_in) in enumerate(zip(active, input_grid_affines)):
+        with_grad = config.view_optimization_mode == "opt-all" or \
+            (config.view_optimization_mode == "opt-current-fix-previous" and i == len(active) - 1)
+        with torch.enable_grad() if with_grad else torch.no_grad():
+            mlp_outs.append(m.mlp_head_from_labels(b_label, num_classes, nifti_affine, ga_in))
+    y_soft, _, y_image, grid_affines, _ = atm_container.acquire_from_labels(
+        b_label, num_classes, b_image, nifti_affine, input_grid_affines, mlp_outs=mlp_outs, modules=active, label_out=None)
+
+    if list(config.slice_fov_vox) != list(config.hires_fov_vox):                     # :193-197 up-sample low-res slices
+        Bv, V, Cc = y_soft.shape[:3]
+        tgt = list(config.hires_fov_vox[:2]) + [1]
+        y_soft = F.interpolate(y_soft.flatten(0, 1), size=tgt, mode="trilinear", align_corners=False).view(Bv, V, Cc, *tgt)
+
+    output_grid_affines = [grid_affines[:, v] for v in range(len(active))]
+    if config.do_augment_recon_orientation and phase in config.aug_phases:           # :303-309
+        s = config.sample_augment_strength
+        output_grid_affines = [apply_affine_augmentation([g], rotation_strength=0.1 * s, zoom_strength=0.2 * s,
+                                                         offset_strength=0.0, generator=generator)[0] for g in output_grid_affines]
+    n_views, n_active = len(config.base_views), len(active)
+    slices = [y_soft[:, v] for v in range(n_active)] + [y_soft[:, n_active - 1]] * (n_views - n_active)      # :321-323
+    output_grid_affines = output_grid_affines + [output_grid_affines[-1]] * (n_views - n_active)
+    b_input = torch.cat(slices, dim=1).squeeze(-1) if n_views != n_active else y_soft.flatten(1, 2).squeeze(-1)   # :325
+    assert b_input.dim() == 4
+    b_target = F.one_hot(b_label.long(), num_classes).permute(0, 4, 1, 2, 3)          # :261-262 (a view, as in the reference)
+    return b_input, b_target, output_grid_affines

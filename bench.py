@@ -266,7 +266,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))    # a hang dies in 2 min, not 10
     nv, V = args.volumes, args.views
     h = make_host_inputs(nv, V, seed=1000 + rank)
     host_lab = h["lab"].pin_memory()
@@ -281,12 +282,12 @@ def run_ours(args):
     soft.requires_grad_(True)
     go = torch.cos(torch.arange(nv * V * NUM_CLASSES * S * S, device=dev, dtype=torch.float32) * 0.618).view(nv, V, NUM_CLASSES, S, S, 1)
     fov_mm, fov_vox = [192.0, 192.0, 1.5], [S, S, 1]
-    LAUNCHES_PER_STEP = 9      # volume_min x2, view_prologue, slice_fwd x3, slice_pad_grad, min_grad_fill, slice_bwd
+    LAUNCHES_PER_STEP = 10     # volume_min_mask, volume_min, view_prologue, slice_fwd x3, slice_pad_grad, min_grad_fill_mask, slice_bwd, view_chain
 
     def step(soft_t, label_t, image_t):
         soft_t.grad = None
         params.grad = None
-        pad_s = AF.volume_min(soft_t)
+        pad_s = AF.volume_min(soft_t, with_mask=True)      # min + 1-bit record for MinBackward (no volume re-read in bwd)
         pad_i = AF.volume_min(image_t)
         ys, yl, yi, ga, nii_o, theta = AF.acquire_views(soft_t, label_t, image_t, nii, gpre, params, init, offset_clip=OFFSET_CLIP,
                                                         zoom_clip=ZOOM_CLIP, spat=S, slice_fov_mm=fov_mm, slice_fov_vox=fov_vox,
@@ -351,10 +352,14 @@ def run_ours(args):
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * nv * V / (e2e_ms.item() / args.e2e_steps / 1e3)
 
+    # All collectives are over: tear the process group down on EVERY rank before any rank-0-only work, so that nothing
+    # below can ever wait on a peer (a stray all_reduce here once hung an 8-GPU run until the NCCL watchdog fired).
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
+    single = world == 1      # breakdown / variants / cpu baseline are reported by the single-GPU run only
 
     # ---- per-kernel breakdown + roofline (rank 0, after the timed regions) ----
     lab_d = host_lab.to(dev)
@@ -362,12 +367,12 @@ def run_ours(args):
     del lab_d
     soft.requires_grad_(True)
     breakdown, roofline, l2_gbs = ({}, None, None)
-    if not args.no_breakdown:
+    if single and not args.no_breakdown:
         breakdown, l2_gbs = kernel_breakdown(AF, dev, soft, label, image, nii, gpre, params, init, go, fov_mm, fov_vox, nv, V)
         roofline = make_roofline(breakdown, l2_gbs)
 
     variants = {}
-    if not args.no_breakdown:
+    if single and not args.no_breakdown:
         del soft, label
         torch.cuda.empty_cache()
         variants["training_case_from_index_labels"] = variant_from_labels(AF, dev, host_lab, host_img, nii, gpre, params, init, go,
@@ -390,15 +395,12 @@ def run_ours(args):
             "gpu_launches": LAUNCHES_PER_STEP * args.steps, "roofline": roofline, "cpu_baseline": cpu_base,
             "kernels": breakdown, "l2_gbs_measured": l2_gbs, "variants": variants}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def variant_from_labels(AF, dev, host_lab, host_img, nii, gpre, params, init, go, fov_mm, fov_vox, nv, V):
     """The reference's TRAINING case (the volume never requires grad, only dTheta is consumed) through the one-hot-from-index
     path: uint8 label map (2 MiB/volume) instead of the fp32 + int64 one-hot volumes (192 MiB/volume); y_soft is bitwise the
     same.  Device-resident and end-to-end (pinned uint8 labels + fp32 image H2D, reduced dTheta + grid affines D2H)."""
-    from acquisition_focus_b200 import parallel as par
     host_u8 = host_lab.to(torch.uint8).pin_memory()
     lab = host_u8.to(dev)
     image = host_img.to(dev)
@@ -411,7 +413,7 @@ def variant_from_labels(AF, dev, host_lab, host_img, nii, gpre, params, init, go
                                                                  offset_clip=OFFSET_CLIP, zoom_clip=ZOOM_CLIP, spat=S,
                                                                  slice_fov_mm=fov_mm, slice_fov_vox=fov_vox)
         torch.autograd.backward([ys], [go])
-        return par.reduce_view_grads(params.grad), ga
+        return params.grad.sum(dim=0), ga                 # no collective here: this runs on one rank only
 
     def e2e():
         g, ga = step(host_u8.to(dev, non_blocking=True), host_img.to(dev, non_blocking=True))
@@ -458,9 +460,9 @@ def kernel_breakdown(AF, dev, soft, label, image, nii, gpre, params, init, go, f
     l2_gbs = buf.numel() * passes / (t * 1e-3) / 1e9
     del buf
     # min pass
-    t = _time(lambda: AF.volume_min(soft), dev)
-    out["volume_min(soft)"] = {"ms": t, "bytes": soft.numel() * 4, "bound": "hbm"}
-    pad_s, pad_i = AF.volume_min(soft), AF.volume_min(image)
+    t = _time(lambda: AF.volume_min(soft, with_mask=True), dev)
+    out["volume_min_mask(soft)"] = {"ms": t, "bytes": soft.numel() * 4 + soft.numel() // 8, "bound": "hbm"}
+    pad_s, pad_i = AF.volume_min(soft, with_mask=True), AF.volume_min(image)
     spec = AF.ViewSpec(kind=L.AFFINE_PARAMS, V=V, gpre=gpre.reshape(nS, 4, 4).contiguous(), init=init, R=R, spat=S,
                        offset_clip=OFFSET_CLIP, zoom_clip=ZOOM_CLIP, nii_affine=nii, fov_mm=tuple(fov_mm),
                        params=params.detach().reshape(nS, NP).contiguous())
@@ -481,8 +483,10 @@ def kernel_breakdown(AF, dev, soft, label, image, nii, gpre, params, init, go, f
     vd, vs = L.volume_desc(sd), spec.struct()
     t = _time(lambda: L.check(lib.afb_slice_pad_grad(C.byref(vd), C.byref(vs), S, S, 1, L.ptr(go), L.ptr(d_pad), st), "afb_slice_pad_grad"), dev)
     out["slice_pad_grad"] = {"ms": t, "bytes": nS * Npix * NUM_CLASSES * 4, "bound": "hbm"}
+    t = _time(lambda: L.check(lib.afb_min_grad_fill_mask(L.ptr(pad_s._afb_mask), sd.numel(), L.ptr(pad_s), L.ptr(d_pad), L.ptr(d_vol), st), "afb_min_grad_fill_mask"), dev)
+    out["min_grad_fill_mask(dVolume)"] = {"ms": t, "bytes": sd.numel() * 4 + sd.numel() // 8, "bound": "hbm"}
     t = _time(lambda: L.check(lib.afb_min_grad_fill(L.ptr(sd), L.F32, sd.numel(), L.ptr(pad_s), L.ptr(d_pad), L.ptr(d_vol), st), "afb_min_grad_fill"), dev)
-    out["min_grad_fill(dVolume)"] = {"ms": t, "bytes": sd.numel() * 8, "bound": "hbm"}
+    out["min_grad_fill(dVolume, re-reads the volume) [not in step]"] = {"ms": t, "bytes": sd.numel() * 8, "bound": "hbm"}
 
     def bwd(with_dvol):
         L.check(lib.afb_slice_bwd(C.byref(vd), C.byref(vs), S, S, 1, L.PAD_DEVICE, 0.0, L.ptr(pad_s), L.ptr(go), None,

@@ -115,6 +115,15 @@ int64_t afb_volume_min_workspace_bytes(void);
 int afb_volume_min(const void* data, int dtype, int64_t n_elements, float* out_min_count,
                    void* workspace, void* stream);
 
+/* fp32 variant that additionally leaves a 1-bit-per-voxel record (per 4096-voxel chunk: its minimum + the bitmask
+ * "== chunk minimum") in `mask` (>= afb_min_mask_bytes(n) bytes, 16-byte aligned).  afb_min_grad_fill_mask rebuilds
+ * MinBackward from it WITHOUT re-reading the volume: 4.1 instead of 8 bytes of HBM traffic per voxel.        */
+int64_t afb_min_mask_bytes(int64_t n_elements);
+int afb_volume_min_mask(const float* data, int64_t n_elements, float* out_min_count, void* mask,
+                        void* workspace, void* stream);
+int afb_min_grad_fill_mask(const void* mask, int64_t n_elements, const float* min_count, const float* d_pad,
+                           float* d_vol, void* stream);
+
 /* ---- view prologue: raw view input -> grid affine, once per acquisition -------------------------
  * Computes for all S = B*V slices what nifti_utils.py:36-71 and learnable_transform.py:144-230,262-289
  * compute on the host in ~100 tiny fp32/fp64 torch ops: state (for the samplers), grid_affine_out

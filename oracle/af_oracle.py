@@ -313,3 +313,34 @@ def skip_connector_sparse(x, b_grid_affines, n_views):
                 acc += val * (wz * wy * ok)[:, None]
         outs.append((acc * wx[:, None]).view(B, c, S, S, S))
     return torch.cat(outs, dim=1).to(x.dtype)
+
+
+# ----------------------------------------------------------------------------
+# a11  per-batch caller                                   running/run_dl.py:238-329
+# ----------------------------------------------------------------------------
+def reconstruction_model_input(b_label, b_image, nifti_affine, base_affine, view_affines, mlp_outs, init, hires_fov_mm,
+                               hires_fov_vox, slice_fov_mm, slice_fov_vox, num_classes, offset_clip, zoom_clip, spat,
+                               aug_affine=None):
+    """Restatement of ``get_reconstruction_model_input`` for ``label_slice_type='from-gt'``, ``opt-all``, all views active:
+    hires resample of label (nearest) and image (bilinear) with ``base_affine`` (:251-259; the image call receives the
+    UPDATED nifti affine, as in the reference), one-hot (:261-264), ``Gpre = base^-1 @ view`` (:227-234) optionally times
+    an augmentation affine (:273-278), per-view ATM tail (:283-312), ``cat`` (:325).  ``mlp_outs[v]`` stands in for the
+    LocalizationNet output of view v."""
+    with torch.no_grad():
+        lab, _, nii = nifti_grid_sample(b_label.unsqueeze(1), nifti_affine, target_fov_mm=hires_fov_mm, target_fov_vox=hires_fov_vox,
+                                        is_label=True, pre_grid_sample_affine=base_affine)
+        img, _, _ = nifti_grid_sample(b_image.unsqueeze(1), nii, target_fov_mm=hires_fov_mm, target_fov_vox=hires_fov_vox,
+                                      is_label=False, pre_grid_sample_affine=base_affine)
+        lab = lab.squeeze(1)
+    label = F.one_hot(lab, num_classes).permute(0, 4, 1, 2, 3)
+    soft = label.float()
+    slices, affines = [], []
+    for v, va in enumerate(view_affines):
+        gpre = input_affine_for_view(base_affine, va).to(nii)
+        if aug_affine is not None:
+            gpre = gpre @ aug_affine.to(gpre)
+        theta = view_theta(mlp_outs[v], init[v:v + 1, :6], init[v, 6:9], init[v:v + 1, 9:], offset_clip, zoom_clip, spat)
+        ys, yl, yi, ga, _ = atm_tail_forward(soft, label, img, nii, gpre.float(), theta, slice_fov_mm, slice_fov_vox)
+        slices.append(ys)
+        affines.append(ga)
+    return torch.cat(slices, dim=1).squeeze(-1), label, affines

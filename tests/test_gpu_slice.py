@@ -205,6 +205,30 @@ def test_min_shift_semantics_and_min_grad(afb):
     assert mc[0].item() == vol.min().item() and mc[1].item() == float((vol == vol.min()).sum())
 
 
+@pytest.mark.parametrize("n", [1, 7, 4096, 4097, 3 * 4096 + 1023, 1_000_003])
+def test_min_mask_record_equals_volume_reread(afb, n):
+    """afb_volume_min_mask + afb_min_grad_fill_mask (1-bit record, no volume re-read) == afb_volume_min + afb_min_grad_fill."""
+    import ctypes as C
+    from acquisition_focus_b200 import _lib as L
+    from acquisition_focus_b200 import functional as AF
+    lib = L.lib()
+    g = torch.Generator().manual_seed(n)
+    vol = torch.randint(0, 5, (n,), generator=g).float() * 0.5 - 1.0        # many ties at the minimum, spread over chunks
+    vol[torch.randint(0, n, (max(1, n // 50),), generator=g)] = -3.25
+    v = vol.cuda()
+    plain, masked = AF.volume_min(v), AF.volume_min(v, with_mask=True)
+    assert torch.equal(plain, masked) and hasattr(masked, "_afb_mask")
+    assert plain[0].item() == vol.min().item() and plain[1].item() == float((vol == vol.min()).sum())
+    d_pad = torch.tensor([2.5], device="cuda")
+    a = torch.full((n,), 7.0, device="cuda"); b = torch.full((n,), 7.0, device="cuda")
+    st = L.stream_ptr(v.device)
+    L.check(lib.afb_min_grad_fill(L.ptr(v), L.F32, n, L.ptr(plain), L.ptr(d_pad), L.ptr(a), st), "fill")
+    L.check(lib.afb_min_grad_fill_mask(L.ptr(masked._afb_mask), n, L.ptr(masked), L.ptr(d_pad), L.ptr(b), st), "fill_mask")
+    assert torch.equal(a, b)
+    want = (vol == vol.min()).float() * (2.5 / float((vol == vol.min()).sum()))
+    assert torch.allclose(a.cpu(), want, rtol=1e-6, atol=0)
+
+
 def test_errors(afb):
     from acquisition_focus_b200._lib import AfbError
     vol = torch.zeros(1, 1, 4, 4, 4)
