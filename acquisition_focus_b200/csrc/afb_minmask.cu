@@ -5,11 +5,11 @@
 // (4 B read + 4 B write per voxel).  The forward's min pass already streams the volume once; this variant makes it
 // also leave behind a 1-bit-per-voxel record that the backward can use instead of the volume:
 //
-//   forward  : per CHUNK of 4096 voxels (16 per thread, held in registers) compute the chunk minimum, then store
-//              chunk_min[chunk] and the bitmask (v == chunk_min) - 2 bytes per thread, +3 % write traffic.
+//   forward  : per CHUNK of 512 voxels (one warp, 16 per lane held in registers) compute the chunk minimum by
+//              shuffles, then store chunk_min[chunk] and the bitmask (v == chunk_min): +4 % write traffic.
 //   backward : a voxel equals the GLOBAL minimum iff its chunk's minimum equals the global minimum AND its bit is set
 //              (chunks with a larger minimum contain no global minimum at all).  The fill therefore reads
-//              4 B + 512 B per chunk instead of 16 KiB: 4.1 B/voxel of traffic instead of 8.
+//              4 B + 64 B per chunk instead of 2 KiB: 4.13 B/voxel of traffic instead of 8.
 //
 // Exact, no speculation.  fp32 volumes only (the only dtype for which the reference's autograd produces dVolume).
 #include "afb_device.cuh"
@@ -17,8 +17,9 @@
 namespace afb {
 
 constexpr int MM_THREADS = 256;
-constexpr int MM_LOADS = 4;                                   // 16-byte loads per thread per chunk
-constexpr int MM_CHUNK = MM_THREADS * MM_LOADS * 4;           // 4096 voxels
+constexpr int MM_LOADS = 4;                                   // 16-byte loads per lane per chunk
+constexpr int MM_CHUNK = 32 * MM_LOADS * 4;                   // 512 voxels per WARP-chunk: the chunk minimum is a pure
+                                                              // shuffle reduction, no CTA barrier in the streaming loop
 constexpr int MM_BLOCKS = 148 * 8;
 
 struct MinCountF { float m, n; };
@@ -28,24 +29,23 @@ __device__ __forceinline__ void mm_merge(float& m, float& n, float m2, float n2)
     else if (m2 == m) { n += n2; }
 }
 
-// mask layout: [n_chunks] float chunk minima, then [n_chunks][256] uint16 (bit 4*j+e of thread t <-> element
-// chunk*4096 + j*1024 + t*4 + e)
+// mask layout: [n_chunks] float chunk minima, then [n_chunks][32] uint16 (bit 4*j+e of lane l <-> element
+// chunk*512 + j*128 + l*4 + e)
 __global__ void __launch_bounds__(MM_THREADS)
 volume_min_mask_kernel(const float* __restrict__ data, long long n, long long n_chunks, float* __restrict__ chunk_min,
                        unsigned short* __restrict__ bits, MinCountF* __restrict__ partial, unsigned* __restrict__ counter,
                        float* __restrict__ out) {
-    __shared__ float s_min[MM_THREADS / 32];
-    __shared__ float s_cmin;
     __shared__ float sm[MM_THREADS / 32], sn[MM_THREADS / 32];
     __shared__ bool last;
     const int t = threadIdx.x, w = t >> 5, lane = t & 31;
-    float gm = INFINITY, gc = 0.0f;                           // this thread's running (min, multiplicity)
-    for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+    const long long warps = (long long)gridDim.x * (MM_THREADS / 32);
+    float gm = INFINITY, gc = 0.0f;                           // this lane's running (min, multiplicity)
+    for (long long ch = (long long)blockIdx.x * (MM_THREADS / 32) + w; ch < n_chunks; ch += warps) {
         const long long base = ch * MM_CHUNK;
         float4 v[MM_LOADS];
 #pragma unroll
         for (int j = 0; j < MM_LOADS; ++j) {
-            const long long e = base + (long long)j * (MM_THREADS * 4) + t * 4;
+            const long long e = base + j * 128 + lane * 4;
             if (e + 3 < n) {
                 v[j] = __ldcs(reinterpret_cast<const float4*>(data + e));
             } else {
@@ -55,34 +55,21 @@ volume_min_mask_kernel(const float* __restrict__ data, long long n, long long n_
                 v[j].w = INFINITY;
             }
         }
-        float m = INFINITY;
+        float c = INFINITY;
 #pragma unroll
-        for (int j = 0; j < MM_LOADS; ++j) m = fminf(fminf(fminf(m, v[j].x), fminf(v[j].y, v[j].z)), v[j].w);
-        float cm = m;
+        for (int j = 0; j < MM_LOADS; ++j) c = fminf(fminf(fminf(c, v[j].x), fminf(v[j].y, v[j].z)), v[j].w);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cm = fminf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
-        if (lane == 0) s_min[w] = cm;
-        __syncthreads();
-        if (t == 0) {
-            float r = s_min[0];
-#pragma unroll
-            for (int k = 1; k < MM_THREADS / 32; ++k) r = fminf(r, s_min[k]);
-            s_cmin = r;
-            chunk_min[ch] = r;
-        }
-        __syncthreads();
-        const float c = s_cmin;
+        for (int o = 16; o > 0; o >>= 1) c = fminf(c, __shfl_xor_sync(0xffffffffu, c, o));
         unsigned b = 0u;
-        float cnt = 0.0f;
 #pragma unroll
         for (int j = 0; j < MM_LOADS; ++j) {
             const unsigned q = (v[j].x == c ? 1u : 0u) | (v[j].y == c ? 2u : 0u) | (v[j].z == c ? 4u : 0u) | (v[j].w == c ? 8u : 0u);
             b |= q << (4 * j);
-            cnt += (float)__popc(q);
         }
-        bits[ch * MM_THREADS + t] = (unsigned short)b;
-        mm_merge(gm, gc, c, cnt);                             // chunk minimum with this thread's share of its multiplicity
-        // (threads whose elements do not attain c contribute cnt = 0, which is what the merge of equal minima needs)
+        bits[ch * 32 + lane] = (unsigned short)b;
+        if (lane == 0) chunk_min[ch] = c;
+        // chunk minimum with this lane's share of its multiplicity (lanes that do not attain c contribute 0)
+        mm_merge(gm, gc, c, (float)__popc(b));
     }
     // CTA reduction of (min, multiplicity), then the last CTA reduces the per-CTA partials
 #pragma unroll
@@ -90,7 +77,6 @@ volume_min_mask_kernel(const float* __restrict__ data, long long n, long long n_
         const float m2 = __shfl_xor_sync(0xffffffffu, gm, o), n2 = __shfl_xor_sync(0xffffffffu, gc, o);
         mm_merge(gm, gc, m2, n2);
     }
-    __syncthreads();
     if (lane == 0) { sm[w] = gm; sn[w] = gc; }
     __syncthreads();
     if (t == 0) {
@@ -130,18 +116,19 @@ min_grad_fill_mask_kernel(const float* __restrict__ chunk_min, const unsigned sh
                           long long n_chunks, const float* __restrict__ min_count, const float* __restrict__ d_pad,
                           float* __restrict__ d_vol) {
     const float m = __ldg(min_count), share = __ldg(d_pad) / __ldg(min_count + 1);
-    const int t = threadIdx.x;
-    for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long warps = (long long)gridDim.x * (MM_THREADS / 32);
+    for (long long ch = (long long)blockIdx.x * (MM_THREADS / 32) + w; ch < n_chunks; ch += warps) {
         const bool hot = __ldg(chunk_min + ch) == m;
-        const unsigned b = hot ? (unsigned)__ldg(bits + ch * MM_THREADS + t) : 0u;
+        const unsigned b = hot ? (unsigned)__ldg(bits + ch * 32 + lane) : 0u;
         const long long base = ch * MM_CHUNK;
 #pragma unroll
         for (int j = 0; j < MM_LOADS; ++j) {
-            const long long e = base + (long long)j * (MM_THREADS * 4) + t * 4;
+            const long long e = base + j * 128 + lane * 4;
             const unsigned q = (b >> (4 * j)) & 15u;
             const float4 o = make_float4((q & 1u) ? share : 0.0f, (q & 2u) ? share : 0.0f, (q & 4u) ? share : 0.0f, (q & 8u) ? share : 0.0f);
             if (e + 3 < n) {
-                *reinterpret_cast<float4*>(d_vol + e) = o;
+                __stcs(reinterpret_cast<float4*>(d_vol + e), o);
             } else {
                 if (e + 0 < n) d_vol[e + 0] = o.x;
                 if (e + 1 < n) d_vol[e + 1] = o.y;
@@ -159,7 +146,7 @@ static long long mm_chunks(long long n) { return (n + MM_CHUNK - 1) / MM_CHUNK; 
 
 extern "C" int64_t afb_min_mask_bytes(int64_t n_elements) {
     const long long c = mm_chunks(n_elements);
-    return (int64_t)(((c * (long long)sizeof(float) + 15) / 16) * 16 + c * MM_THREADS * (long long)sizeof(unsigned short));
+    return (int64_t)(((c * (long long)sizeof(float) + 15) / 16) * 16 + c * 32 * (long long)sizeof(unsigned short));
 }
 
 extern "C" int afb_volume_min_mask(const float* data, int64_t n, float* out_min_count, void* mask, void* workspace, void* stream) {
@@ -173,7 +160,8 @@ extern "C" int afb_volume_min_mask(const float* data, int64_t n, float* out_min_
     MinCountF* partial = (MinCountF*)((char*)workspace + 16);
     cudaError_t e = cudaMemsetAsync(counter, 0, 16, st);
     if (e != cudaSuccess) return (int)e;
-    const int blocks = (int)(c < MM_BLOCKS ? c : MM_BLOCKS);
+    const long long wantb = (c + MM_THREADS / 32 - 1) / (MM_THREADS / 32);
+    const int blocks = (int)(wantb < MM_BLOCKS ? wantb : MM_BLOCKS);
     volume_min_mask_kernel<<<blocks, MM_THREADS, 0, st>>>(data, n, c, chunk_min, bits, partial, counter, out_min_count);
     return (int)cudaGetLastError();
 }
@@ -184,7 +172,8 @@ extern "C" int afb_min_grad_fill_mask(const void* mask, int64_t n, const float* 
     const long long c = mm_chunks(n);
     const float* chunk_min = (const float*)mask;
     const unsigned short* bits = (const unsigned short*)((const char*)mask + ((c * (long long)sizeof(float) + 15) / 16) * 16);
-    const int blocks = (int)(c < 148 * 16 ? c : 148 * 16);
+    const long long wantb = (c + MM_THREADS / 32 - 1) / (MM_THREADS / 32);
+    const int blocks = (int)(wantb < 148 * 16 ? wantb : 148 * 16);
     min_grad_fill_mask_kernel<<<blocks, MM_THREADS, 0, (cudaStream_t)stream>>>(chunk_min, bits, n, c, min_count, d_pad, d_vol);
     return (int)cudaGetLastError();
 }

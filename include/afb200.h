@@ -115,7 +115,7 @@ int64_t afb_volume_min_workspace_bytes(void);
 int afb_volume_min(const void* data, int dtype, int64_t n_elements, float* out_min_count,
                    void* workspace, void* stream);
 
-/* fp32 variant that additionally leaves a 1-bit-per-voxel record (per 4096-voxel chunk: its minimum + the bitmask
+/* fp32 variant that additionally leaves a 1-bit-per-voxel record (per 512-voxel chunk: its minimum + the bitmask
  * "== chunk minimum") in `mask` (>= afb_min_mask_bytes(n) bytes, 16-byte aligned).  afb_min_grad_fill_mask rebuilds
  * MinBackward from it WITHOUT re-reading the volume: 4.1 instead of 8 bytes of HBM traffic per voxel.        */
 int64_t afb_min_mask_bytes(int64_t n_elements);
