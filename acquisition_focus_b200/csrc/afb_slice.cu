@@ -122,60 +122,6 @@ slice_fwd_cl_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad
     }
 }
 
-// Lane-pair variant of the channels-last bilinear forward (C % 8 == 0): two adjacent lanes share one output
-// location and each gathers one 16-byte half of every corner's 32-byte (8 x fp32) sector, so one warp-wide load
-// instruction covers 16 full sectors instead of 32 half sectors (half the distinct lines per request through L1,
-// which is what bounds the one-lane-per-location kernel at ~63 % L1 throughput).  CTA tile 16 cols x 8 rows, warp
-// patch 8 x 2 (a 32-byte output row segment per channel plane).  Same arithmetic, bitwise the same results.
-__device__ __forceinline__ Pix pixel_of_lane_pair(const OutGeom& g, int tiles_c2) {
-    const int tid = threadIdx.x;
-    const int w = tid >> 5, p = (tid & 31) >> 1;
-    const int lc = ((w & 1) << 3) + (p & 7);
-    const int lr = ((w >> 1) << 1) + (p >> 3);
-    const int tr = blockIdx.x / tiles_c2, tc = blockIdx.x % tiles_c2;
-    const int row = tr * 8 + lr, col = tc * 16 + lc;
-    Pix px;
-    px.valid = row < g.rows && col < g.cols;
-    if (g.Wo == 1) { px.i = row; px.j = col; px.k = 0; } else { px.i = row / g.Ho; px.j = row % g.Ho; px.k = col; }
-    return px;
-}
-
-__global__ void __launch_bounds__(NTHREADS, 3)
-slice_fwd_cl_pair_kernel(VolArgs vol, ViewArgs va, OutGeom g, int tiles_c2, int pad_mode, float pad_value,
-                         const float* pad_device, float* __restrict__ out) {
-    const int s = blockIdx.y;
-    const Pix p = pixel_of_lane_pair(g, tiles_c2);
-    if (!p.valid) return;
-    const int half = (threadIdx.x & 1) << 2;                   // this lane's 4 of every 8 channels
-    const Sample sm = sample_coords(g, p, va, s, vol);
-    const int b = s / va.V;
-    const float* __restrict__ src = (const float*)vol.data + (long long)b * vol.sB;
-    const size_t plane = (size_t)g.Do * g.Ho * g.Wo;
-    float* __restrict__ dst = out + (size_t)s * vol.C * plane + ((size_t)p.i * g.Ho + p.j) * g.Wo + p.k;
-    const Corners cn = corners_of(sm, vol);
-    const float pad = pad_of(pad_mode, pad_value, pad_device);
-    for (int c0 = half; c0 < vol.C; c0 += 8) {
-        float4 v[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            v[k] = cn.in(k) ? __ldg(reinterpret_cast<const float4*>(src + cn.off(k, vol) + c0)) : make_float4(pad, pad, pad, pad);
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (cn.in(k)) {
-                const float wk = cn.w(k);
-                a0 = __fadd_rn(a0, __fmul_rn(__fsub_rn(v[k].x, pad), wk));
-                a1 = __fadd_rn(a1, __fmul_rn(__fsub_rn(v[k].y, pad), wk));
-                a2 = __fadd_rn(a2, __fmul_rn(__fsub_rn(v[k].z, pad), wk));
-                a3 = __fadd_rn(a3, __fmul_rn(__fsub_rn(v[k].w, pad), wk));
-            }
-        dst[(size_t)(c0 + 0) * plane] = __fadd_rn(a0, pad);
-        dst[(size_t)(c0 + 1) * plane] = __fadd_rn(a1, pad);
-        dst[(size_t)(c0 + 2) * plane] = __fadd_rn(a2, pad);
-        dst[(size_t)(c0 + 3) * plane] = __fadd_rn(a3, pad);
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // backward: re-gather, dVolume scatter (RED), dGrid -> 12 sums of dgrid (x) base per slice.
 // CTA reduction (shuffle -> smem) then one fp64 atomic per sum per CTA into the per-slice workspace;
@@ -270,56 +216,6 @@ slice_bwd_cl_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad
     bwd_reduce(s, part, pad_mode, d_pad, ws_acc);
 }
 
-// lane-pair variant of the channels-last backward (see slice_fwd_cl_pair_kernel): each lane of a pair re-gathers and
-// scatters one 16-byte half of every corner sector; the dgrid sums are linear in the per-channel dots, so every lane
-// simply contributes the partial sums of its own 4 channels to the CTA reduction.
-__global__ void __launch_bounds__(NTHREADS, 2)
-slice_bwd_cl_pair_kernel(VolArgs vol, ViewArgs va, OutGeom g, int tiles_c2, int pad_mode, float pad_value,
-                         const float* pad_device, const float* __restrict__ grad_out, float* __restrict__ d_vol,
-                         float* __restrict__ d_pad, double* __restrict__ ws_acc) {
-    const int s = blockIdx.y;
-    float part[13];
-#pragma unroll
-    for (int q = 0; q < 13; ++q) part[q] = 0.0f;
-    const Pix p = pixel_of_lane_pair(g, tiles_c2);
-    if (p.valid) {
-        const int half = (threadIdx.x & 1) << 2;
-        const Sample sm = sample_coords(g, p, va, s, vol);
-        const Corners cn = corners_of(sm, vol);
-        const float pad = pad_of(pad_mode, pad_value, pad_device);
-        const int b = s / va.V;
-        const float* __restrict__ src = (const float*)vol.data + (long long)b * vol.sB;
-        float* __restrict__ dv = d_vol ? d_vol + (long long)b * vol.sB : nullptr;
-        const size_t plane = (size_t)g.Do * g.Ho * g.Wo;
-        const float* __restrict__ go_p = grad_out + (size_t)s * vol.C * plane + ((size_t)p.i * g.Ho + p.j) * g.Wo + p.k;
-        float dot[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) dot[k] = 0.0f;
-        float gsum = 0.0f;
-        for (int c0 = half; c0 < vol.C; c0 += 8) {
-            const float g0 = __ldg(go_p + (size_t)(c0 + 0) * plane), g1 = __ldg(go_p + (size_t)(c0 + 1) * plane);
-            const float g2 = __ldg(go_p + (size_t)(c0 + 2) * plane), g3 = __ldg(go_p + (size_t)(c0 + 3) * plane);
-            gsum += (g0 + g1) + (g2 + g3);
-            float4 v[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                v[k] = cn.in(k) ? __ldg(reinterpret_cast<const float4*>(src + cn.off(k, vol) + c0)) : make_float4(pad, pad, pad, pad);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                if (cn.in(k)) {
-                    dot[k] = fmaf(v[k].x - pad, g0, fmaf(v[k].y - pad, g1, fmaf(v[k].z - pad, g2, fmaf(v[k].w - pad, g3, dot[k]))));
-                    if (dv) {
-                        const float wk = cn.w(k);
-                        atomicAdd(reinterpret_cast<float4*>(dv + cn.off(k, vol) + c0), make_float4(wk * g0, wk * g1, wk * g2, wk * g3));
-                    }
-                }
-            }
-        }
-        grid_grad_parts(dot, cn, sm, vol, gsum, part);
-    }
-    bwd_reduce(s, part, pad_mode, d_pad, ws_acc);
-}
-
 // d(out)/d(pad) = sum go * (1 - sum of in-bounds weights): depends on geometry and grad_out only, so it can run
 // BEFORE the dVolume fill, which lets MinBackward be fused with the zero-fill (afb_min_grad_fill).
 __global__ void __launch_bounds__(NTHREADS, 4)
@@ -365,12 +261,6 @@ static int make_args(const afb_volume* vol, const afb_views* views, int Do, int 
     return make_view_args(views, vol->B, vol->D, vol->H, vol->W, Do, Ho, Wo, /*need_state=*/true, a);
 }
 
-// tuning knob (measurement only): AFB_CL_PAIR=0 selects the one-lane-per-location channels-last kernels
-static bool lane_pair_enabled() {
-    static const int v = [] { const char* e = getenv("AFB_CL_PAIR"); return e ? atoi(e) : 1; }();
-    return v != 0;
-}
-
 // channels-last fast path: channels contiguous, everything 16-byte aligned
 static bool channels_last_ok(const afb_volume* vol, int n, const void* extra_ptr) {
     if (vol->sC != 1 || vol->C % n != 0) return false;
@@ -386,15 +276,10 @@ static int launch_fwd(const afb_volume* vol, const VolArgs& v, const ViewArgs& a
     const dim3 grid = slice_grid(g, S);
     const bool cl = channels_last_ok(vol, 16 / (int)sizeof(T), nullptr) && (mode == AFB_NEAREST || std::is_same<T, float>::value);
     if (cl) {
-        if (mode == AFB_NEAREST) {
+        if (mode == AFB_NEAREST)
             slice_fwd_cl_kernel<T, AFB_NEAREST><<<grid, NTHREADS, 0, st>>>(v, a, g, pad_mode, pad_value, pad_device, (T*)out);
-        } else if (std::is_same<T, float>::value && v.C % 8 == 0 && lane_pair_enabled()) {
-            const int tiles_c2 = (g.cols + 15) / 16;
-            const dim3 grid2(((g.rows + 7) / 8) * tiles_c2, S);
-            slice_fwd_cl_pair_kernel<<<grid2, NTHREADS, 0, st>>>(v, a, g, tiles_c2, pad_mode, pad_value, pad_device, (float*)out);
-        } else {
+        else
             slice_fwd_cl_kernel<T, AFB_BILINEAR><<<grid, NTHREADS, 0, st>>>(v, a, g, pad_mode, pad_value, pad_device, (T*)out);
-        }
     } else if (mode == AFB_NEAREST) {
         slice_fwd_kernel<T, AFB_NEAREST><<<grid, NTHREADS, 0, st>>>(v, a, g, pad_mode, pad_value, pad_device, (T*)out);
     } else {
@@ -455,15 +340,10 @@ extern "C" int afb_slice_bwd(const afb_volume* vol, const afb_views* views, int 
 #define AFB_BWD(T) slice_bwd_kernel<T><<<grid, NTHREADS, 0, st>>>(v, a, g, pad_mode, pad_value, pad_device, grad_out, d_vol, d_pad, acc)
         switch (vol->dtype) {
             case AFB_F32:
-                if (channels_last_ok(vol, 4, d_vol) && v.C % 8 == 0 && lane_pair_enabled()) {
-                    const int tiles_c2 = (g.cols + 15) / 16;
-                    const dim3 grid2(((g.rows + 7) / 8) * tiles_c2, S);
-                    slice_bwd_cl_pair_kernel<<<grid2, NTHREADS, 0, st>>>(v, a, g, tiles_c2, pad_mode, pad_value, pad_device, grad_out, d_vol, d_pad, acc);
-                } else if (channels_last_ok(vol, 4, d_vol)) {
+                if (channels_last_ok(vol, 4, d_vol))
                     slice_bwd_cl_kernel<<<grid, NTHREADS, 0, st>>>(v, a, g, pad_mode, pad_value, pad_device, grad_out, d_vol, d_pad, acc);
-                } else {
+                else
                     AFB_BWD(float);
-                }
                 break;
             case AFB_BF16: AFB_BWD(__nv_bfloat16); break;
             case AFB_F16: AFB_BWD(__half); break;

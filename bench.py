@@ -287,11 +287,9 @@ def run_ours(args):
     def step(soft_t, label_t, image_t):
         soft_t.grad = None
         params.grad = None
-        pad_s = AF.volume_min(soft_t, with_mask=True)      # min + 1-bit record for MinBackward (no volume re-read in bwd)
-        pad_i = AF.volume_min(image_t)
+        # the public call: the min passes (reference min-shift semantics), the shared view prologue and the three slicings
         ys, yl, yi, ga, nii_o, theta = AF.acquire_views(soft_t, label_t, image_t, nii, gpre, params, init, offset_clip=OFFSET_CLIP,
-                                                        zoom_clip=ZOOM_CLIP, spat=S, slice_fov_mm=fov_mm, slice_fov_vox=fov_vox,
-                                                        soft_pad=pad_s, image_pad=pad_i)
+                                                        zoom_clip=ZOOM_CLIP, spat=S, slice_fov_mm=fov_mm, slice_fov_vox=fov_vox)
         torch.autograd.backward([ys], [go])
         g = par.reduce_view_grads(params.grad)          # [V,NP]; NCCL all-reduce when world > 1
         return g, ga
