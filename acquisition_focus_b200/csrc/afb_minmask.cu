@@ -161,11 +161,7 @@ extern "C" int afb_volume_min_mask(const float* data, int64_t n, float* out_min_
     cudaError_t e = cudaMemsetAsync(counter, 0, 16, st);
     if (e != cudaSuccess) return (int)e;
     const long long wantb = (c + MM_THREADS / 32 - 1) / (MM_THREADS / 32);
-    // CTAs per SM of this persistent, HBM-bound pass: fewer than the 8 that fit leaves room for the latency-bound gathers
-    // that the host runs concurrently on a side stream (AFB_MIN_CTAS_PER_SM, 1..8, is a measurement knob)
-    static const int per_sm = [] { const char* e = getenv("AFB_MIN_CTAS_PER_SM"); int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
-    const int cap = 148 * per_sm;
-    const int blocks = (int)(wantb < cap ? wantb : cap);
+    const int blocks = (int)(wantb < MM_BLOCKS ? wantb : MM_BLOCKS);
     volume_min_mask_kernel<<<blocks, MM_THREADS, 0, st>>>(data, n, c, chunk_min, bits, partial, counter, out_min_count);
     return (int)cudaGetLastError();
 }

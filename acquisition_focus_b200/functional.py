@@ -42,22 +42,6 @@ def _is_dense(t: torch.Tensor) -> bool:
     return True
 
 
-_SIDE_STREAMS = {}
-
-
-def _side_stream(device) -> torch.cuda.Stream:
-    """One side stream per device for overlapping the latency-bound gathers with the HBM-bound volume passes."""
-    key = torch.device(device).index
-    if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
-    return _SIDE_STREAMS[key]
-
-
-def _overlap_enabled() -> bool:
-    import os
-    return os.environ.get("AFB_OVERLAP", "1") != "0"
-
-
 def _zeros_like_strided(t: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
     out = torch.empty_strided(t.shape, t.stride(), dtype=dtype, device=t.device)
     return out.zero_()
@@ -328,36 +312,13 @@ def acquire_views(x_soft_label, x_label, x_image, nifti_affine, gpre, params, in
     p = params.to(dev, torch.float32).reshape(B * V, NP)
     spec = spec.replace(params=p.detach().contiguous())
     prepared = prepare_views(spec, B, x_soft_label.shape[2:], slice_fov_vox, dev)      # one prologue for everything below
-    has_label = x_label is not None and x_label.numel() > 0
-    has_image = x_image is not None and x_image.numel() > 0
-    y_label = y_image = None
-
-    def side_work():
-        yl = yi = None
-        with torch.no_grad():
-            if has_label:
-                yl = _run_slice(x_label, p.detach(), spec, slice_fov_vox, L.NEAREST, "zero", prepared)[0]
-            if has_image:
-                yi = _run_slice(x_image, p.detach(), spec, slice_fov_vox, L.BILINEAR, image_pad, prepared)[0]
-        return yl, yi
-
-    # The soft-label path starts with an HBM-bound pass (the min over the whole volume) that needs few SM resources,
-    # while the label / image slicings are latency-bound gathers: run those on a side stream so the two overlap.
-    overlap = _overlap_enabled() and (has_label or has_image) and soft_pad == "global_min"
-    if overlap:
-        main = torch.cuda.current_stream(dev)
-        side = _side_stream(dev)
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            y_label, y_image = side_work()
     y_soft, ga, nii, theta = _run_slice(x_soft_label, p, spec, slice_fov_vox, L.BILINEAR, soft_pad, prepared)
-    if overlap:
-        main.wait_stream(side)
-        for t in (y_label, y_image):
-            if t is not None:
-                t.record_stream(main)
-    else:
-        y_label, y_image = side_work()
+    y_label = y_image = None
+    with torch.no_grad():
+        if x_label is not None and x_label.numel() > 0:
+            y_label = _run_slice(x_label, p.detach(), spec, slice_fov_vox, L.NEAREST, "zero", prepared)[0]
+        if x_image is not None and x_image.numel() > 0:
+            y_image = _run_slice(x_image, p.detach(), spec, slice_fov_vox, L.BILINEAR, image_pad, prepared)[0]
     return y_soft, y_label, y_image, ga, nii, theta
 
 
