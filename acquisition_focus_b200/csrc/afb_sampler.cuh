@@ -64,6 +64,43 @@ __device__ __forceinline__ Sample sample_coords(const OutGeom& g, const Pix& p, 
     return sm;
 }
 
+// 16-byte channel vectors of the channels-last kernels: how many elements, and how to widen them to fp32
+template <typename T> struct Vec16 {
+    static constexpr int N = 16 / (int)sizeof(T);
+    static constexpr bool is_float = false;
+};
+template <> struct Vec16<float> {
+    static constexpr int N = 4;
+    static constexpr bool is_float = true;
+    static __device__ __forceinline__ void decode(const uint4& r, float* o) {
+        o[0] = __uint_as_float(r.x); o[1] = __uint_as_float(r.y); o[2] = __uint_as_float(r.z); o[3] = __uint_as_float(r.w);
+    }
+};
+template <> struct Vec16<__nv_bfloat16> {
+    static constexpr int N = 8;
+    static constexpr bool is_float = true;
+    static __device__ __forceinline__ void decode(const uint4& r, float* o) {
+        const unsigned w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {           // bf16 -> fp32 is a 16-bit shift
+            o[2 * i] = __uint_as_float(w[i] << 16);
+            o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+};
+template <> struct Vec16<__half> {
+    static constexpr int N = 8;
+    static constexpr bool is_float = true;
+    static __device__ __forceinline__ void decode(const uint4& r, float* o) {
+        const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(h[i]);
+            o[2 * i] = f.x; o[2 * i + 1] = f.y;
+        }
+    }
+};
+
 // The 8 trilinear corners of one sample, kept lean (one base offset + 6 axis weights + in-bounds mask);
 // corner k = (dx,dy,dz) = (k&1, (k>>1)&1, k>>2) is ATen's order tnw,tne,tsw,tse,bnw,bne,bsw,bse.
 // Weights are formed exactly as ATen does: (wx*wy)*wz.

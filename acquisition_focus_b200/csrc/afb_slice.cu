@@ -81,7 +81,7 @@ slice_fwd_cl_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad
     const T* __restrict__ src = (const T*)vol.data + (long long)b * vol.sB;
     const size_t plane = (size_t)g.Do * g.Ho * g.Wo;
     T* __restrict__ dst = out + (size_t)s * vol.C * plane + ((size_t)p.i * g.Ho + p.j) * g.Wo + p.k;
-    constexpr int N = 16 / (int)sizeof(T);
+    constexpr int N = Vec16<T>::N;
 
     if (MODE == AFB_NEAREST) {
         const int xn = __float2int_rn(sm.ix), yn = __float2int_rn(sm.iy), zn = __float2int_rn(sm.iz);
@@ -96,28 +96,29 @@ slice_fwd_cl_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad
         }
         return;
     }
-    if constexpr (std::is_same<T, float>::value && MODE == AFB_BILINEAR) {
+    if constexpr (Vec16<T>::is_float && MODE == AFB_BILINEAR) {
+        // fp32: 4 channels per 16-byte load; bf16 / fp16 storage: 8 (fp32 coordinates, weights and accumulation)
         const Corners cn = corners_of(sm, vol);
         const float pad = pad_of(pad_mode, pad_value, pad_device);
-        for (int c0 = 0; c0 < vol.C; c0 += 4) {
-            float4 v[8];
+        for (int c0 = 0; c0 < vol.C; c0 += N) {
+            uint4 raw[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-                v[k] = cn.in(k) ? __ldg(reinterpret_cast<const float4*>(src + cn.off(k, vol) + c0)) : make_float4(pad, pad, pad, pad);
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                raw[k] = cn.in(k) ? __ldg(reinterpret_cast<const uint4*>(src + cn.off(k, vol) + c0)) : make_uint4(0u, 0u, 0u, 0u);
+            float acc[N];
+#pragma unroll
+            for (int q = 0; q < N; ++q) acc[q] = 0.0f;
 #pragma unroll
             for (int k = 0; k < 8; ++k)
                 if (cn.in(k)) {
+                    float vv[N];
+                    Vec16<T>::decode(raw[k], vv);
                     const float wk = cn.w(k);
-                    a0 = __fadd_rn(a0, __fmul_rn(__fsub_rn(v[k].x, pad), wk));
-                    a1 = __fadd_rn(a1, __fmul_rn(__fsub_rn(v[k].y, pad), wk));
-                    a2 = __fadd_rn(a2, __fmul_rn(__fsub_rn(v[k].z, pad), wk));
-                    a3 = __fadd_rn(a3, __fmul_rn(__fsub_rn(v[k].w, pad), wk));
+#pragma unroll
+                    for (int q = 0; q < N; ++q) acc[q] = __fadd_rn(acc[q], __fmul_rn(__fsub_rn(vv[q], pad), wk));
                 }
-            dst[(size_t)(c0 + 0) * plane] = __fadd_rn(a0, pad);
-            dst[(size_t)(c0 + 1) * plane] = __fadd_rn(a1, pad);
-            dst[(size_t)(c0 + 2) * plane] = __fadd_rn(a2, pad);
-            dst[(size_t)(c0 + 3) * plane] = __fadd_rn(a3, pad);
+#pragma unroll
+            for (int q = 0; q < N; ++q) dst[(size_t)(c0 + q) * plane] = Store<T>::from_float(__fadd_rn(acc[q], pad));
         }
     }
 }
@@ -170,10 +171,12 @@ slice_bwd_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad_va
 }
 
 // channels-last fp32 volumes: 16-byte gathers and 16-byte vector reductions (red.global.add.v4.f32)
+template <typename T>
 __global__ void __launch_bounds__(NTHREADS, 2)
 slice_bwd_cl_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad_value, const float* pad_device,
                     const float* __restrict__ grad_out, float* __restrict__ d_vol, float* __restrict__ d_pad,
                     double* __restrict__ ws_acc) {
+    constexpr int N = Vec16<T>::N;
     const int s = blockIdx.y;
     float part[13];
 #pragma unroll
@@ -184,7 +187,7 @@ slice_bwd_cl_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad
         const Corners cn = corners_of(sm, vol);
         const float pad = pad_of(pad_mode, pad_value, pad_device);
         const int b = s / va.V;
-        const float* __restrict__ src = (const float*)vol.data + (long long)b * vol.sB;
+        const T* __restrict__ src = (const T*)vol.data + (long long)b * vol.sB;
         float* __restrict__ dv = d_vol ? d_vol + (long long)b * vol.sB : nullptr;
         const size_t plane = (size_t)g.Do * g.Ho * g.Wo;
         const float* __restrict__ go_p = grad_out + (size_t)s * vol.C * plane + ((size_t)p.i * g.Ho + p.j) * g.Wo + p.k;
@@ -192,21 +195,27 @@ slice_bwd_cl_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad
 #pragma unroll
         for (int k = 0; k < 8; ++k) dot[k] = 0.0f;
         float gsum = 0.0f;
-        for (int c0 = 0; c0 < vol.C; c0 += 4) {
-            const float g0 = __ldg(go_p + (size_t)(c0 + 0) * plane), g1 = __ldg(go_p + (size_t)(c0 + 1) * plane);
-            const float g2 = __ldg(go_p + (size_t)(c0 + 2) * plane), g3 = __ldg(go_p + (size_t)(c0 + 3) * plane);
-            gsum += (g0 + g1) + (g2 + g3);
-            float4 v[8];
+        for (int c0 = 0; c0 < vol.C; c0 += N) {
+            float go[N];
+#pragma unroll
+            for (int q = 0; q < N; ++q) { go[q] = __ldg(go_p + (size_t)(c0 + q) * plane); gsum += go[q]; }
+            uint4 raw[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-                v[k] = cn.in(k) ? __ldg(reinterpret_cast<const float4*>(src + cn.off(k, vol) + c0)) : make_float4(pad, pad, pad, pad);
+                raw[k] = cn.in(k) ? __ldg(reinterpret_cast<const uint4*>(src + cn.off(k, vol) + c0)) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 if (cn.in(k)) {
-                    dot[k] = fmaf(v[k].x - pad, g0, fmaf(v[k].y - pad, g1, fmaf(v[k].z - pad, g2, fmaf(v[k].w - pad, g3, dot[k]))));
+                    float vv[N];
+                    Vec16<T>::decode(raw[k], vv);
+#pragma unroll
+                    for (int q = 0; q < N; ++q) dot[k] = fmaf(vv[q] - pad, go[q], dot[k]);
                     if (dv) {
                         const float wk = cn.w(k);
-                        atomicAdd(reinterpret_cast<float4*>(dv + cn.off(k, vol) + c0), make_float4(wk * g0, wk * g1, wk * g2, wk * g3));
+#pragma unroll
+                        for (int q = 0; q < N; q += 4)
+                            atomicAdd(reinterpret_cast<float4*>(dv + cn.off(k, vol) + c0 + q),
+                                      make_float4(wk * go[q], wk * go[q + 1], wk * go[q + 2], wk * go[q + 3]));
                     }
                 }
             }
@@ -274,7 +283,7 @@ static int launch_fwd(const afb_volume* vol, const VolArgs& v, const ViewArgs& a
                       float pad_value, const float* pad_device, void* out, cudaStream_t st) {
     const int S = v.B * a.V;
     const dim3 grid = slice_grid(g, S);
-    const bool cl = channels_last_ok(vol, 16 / (int)sizeof(T), nullptr) && (mode == AFB_NEAREST || std::is_same<T, float>::value);
+    const bool cl = channels_last_ok(vol, Vec16<T>::N, nullptr) && (mode == AFB_NEAREST || Vec16<T>::is_float);
     if (cl) {
         if (mode == AFB_NEAREST)
             slice_fwd_cl_kernel<T, AFB_NEAREST><<<grid, NTHREADS, 0, st>>>(v, a, g, pad_mode, pad_value, pad_device, (T*)out);
@@ -337,14 +346,13 @@ extern "C" int afb_slice_bwd(const afb_volume* vol, const afb_views* views, int 
     double* acc = (double*)workspace;
     cudaStream_t st = (cudaStream_t)stream;
     if (grad_out) {     // grad_out == NULL: chain-only (nearest / integer volumes): only the upstream grad is propagated
-#define AFB_BWD(T) slice_bwd_kernel<T><<<grid, NTHREADS, 0, st>>>(v, a, g, pad_mode, pad_value, pad_device, grad_out, d_vol, d_pad, acc)
+#define AFB_BWD(T)                                                                                                              \
+    if (channels_last_ok(vol, Vec16<T>::N, d_vol))                                                                              \
+        slice_bwd_cl_kernel<T><<<grid, NTHREADS, 0, st>>>(v, a, g, pad_mode, pad_value, pad_device, grad_out, d_vol, d_pad, acc); \
+    else                                                                                                                        \
+        slice_bwd_kernel<T><<<grid, NTHREADS, 0, st>>>(v, a, g, pad_mode, pad_value, pad_device, grad_out, d_vol, d_pad, acc)
         switch (vol->dtype) {
-            case AFB_F32:
-                if (channels_last_ok(vol, 4, d_vol))
-                    slice_bwd_cl_kernel<<<grid, NTHREADS, 0, st>>>(v, a, g, pad_mode, pad_value, pad_device, grad_out, d_vol, d_pad, acc);
-                else
-                    AFB_BWD(float);
-                break;
+            case AFB_F32: AFB_BWD(float); break;
             case AFB_BF16: AFB_BWD(__nv_bfloat16); break;
             case AFB_F16: AFB_BWD(__half); break;
             default: return AFB_EDTYPE;

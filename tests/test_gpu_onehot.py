@@ -47,6 +47,46 @@ def test_from_labels_bitwise_vs_dense_path(afb, S, dt):
     assert idx.dtype == torch.uint8 and torch.equal(idx.long(), dense[1].argmax(2))
 
 
+def test_cfg5_256_dense_and_label_paths_vs_oracle(afb):
+    """configs[4] size: 256^3 volume, 256^2 slices, C=8, fp32 and bf16 storage; checked against the oracle port on
+    the same inputs (forward bitwise given the same grid affine; dTheta 1e-4; bf16 after rounding, 2^-8)."""
+    import torch.nn.functional as F
+    S, V, C = 256, 2, 8
+    gen = torch.Generator().manual_seed(5)
+    lab = torch.randint(0, C, (1, S // 8, S // 8, S // 8), generator=gen)
+    lab = lab.repeat_interleave(8, 1).repeat_interleave(8, 2).repeat_interleave(8, 3)          # blocky 256^3 label map
+    label, soft = cases.one_hot_volumes(lab, C)
+    syn = cases.synthetic
+    gpre = torch.stack([syn.phantom_view_affines()["p2CH"] @ syn.random_aug_affine(gen, 0.3, 0.2, 0.0) for _ in range(V)])[None]
+    R = 51
+    params = torch.cat([torch.tensor([1.0, 0, 0, 0, 1.0, 0]) + 0.3 * torch.randn(1, V, 6, generator=gen),
+                        torch.randn(1, V, 3 * R, generator=gen), torch.randn(1, V, 1, generator=gen)], -1)
+    nii = syn.default_nifti_affine(1, 0.75)
+    kw = dict(offset_clip=0.2, zoom_clip=0.0, spat=S, slice_fov_mm=[192.0, 192.0, 0.75], slice_fov_vox=[S, S, 1])
+    init = INIT.repeat(V, 1)
+    p_fast = params.cuda().requires_grad_(True)
+    ys, yl, _, ga, _, _ = afb.acquire_views_from_labels(lab.to(torch.uint8).cuda(), None, nii.cuda(), gpre.cuda(), p_fast, init.cuda(),
+                                                        num_classes=C, **kw)
+    go = cases.pattern(ys.shape, 1.0)
+    (ys * go.cuda()).sum().backward()
+    p_dense = params.cuda().requires_grad_(True)
+    yd = afb.acquire_views(soft.cuda(), None, None, nii.cuda(), gpre.cuda(), p_dense, init.cuda(), **kw)[0]
+    (yd * go.cuda()).sum().backward()
+    assert torch.equal(ys, yd)
+    assert (p_fast.grad - p_dense.grad).abs().max().item() <= 1e-5 * p_dense.grad.abs().max().item()
+    yb = afb.acquire_views(soft.to(torch.bfloat16).cuda(), None, None, nii.cuda(), gpre.cuda(), params.cuda(), init.cuda(), **kw)[0]
+    assert yb.dtype == torch.bfloat16 and (yb.float() - yd.detach().to(torch.bfloat16).float()).abs().max().item() <= 2.0 ** -7
+    for v in range(V):          # oracle: the kernel's own grid affine through ATen (bitwise), dTheta through the full chain
+        grid = F.affine_grid(ga[:, v, :3, :].cpu(), [1, C, S, S, 1], align_corners=False)
+        assert torch.equal(ys[:, v].detach().cpu(), F.grid_sample(soft, grid, mode="bilinear", padding_mode="zeros", align_corners=False))
+        assert torch.equal(yl[:, v].cpu(), F.grid_sample(label.float(), grid, mode="nearest", padding_mode="zeros", align_corners=False).long())
+        p = params[:, v].clone().requires_grad_(True)
+        theta = O.view_theta(p, INIT[:, :6], INIT[0, 6:9], INIT[:, 9:], 0.2, 0.0, S)
+        rs = O.atm_tail_forward(soft, None, None, nii, gpre[:, v], theta, torch.tensor(kw["slice_fov_mm"]), torch.tensor(kw["slice_fov_vox"]))[0]
+        (rs * go[:, v]).sum().backward()
+        assert (p_fast.grad[:, v].cpu() - p.grad).abs().max().item() <= 1e-4 * p.grad.abs().max().item()
+
+
 def test_from_labels_vs_oracle(afb):
     """Directly against the oracle port of the reference (one view at a time, as the reference loops)."""
     case = cases.atm_case(32, 2, 3, seed=71, zoom_clip=0.25)

@@ -164,6 +164,32 @@ def test_half_storage(afb, dt, rel):
     close(v.grad.float(), vr.grad, 1e-2)
 
 
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])
+def test_channels_last_kernels_equal_generic_kernels(afb, dt):
+    """The 16-byte vector (channels-last) kernels and the generic strided kernels run the same per-channel arithmetic:
+    forward bitwise equal, gradients equal up to atomic ordering; for every floating storage type."""
+    B, S, C = 2, 28, 8
+    base = cases.randn((B, S, S, S, C), 57).to(dt)
+    cl = base.permute(0, 4, 1, 2, 3).cuda()                   # channels-last view  (sC == 1)
+    pl = cl.contiguous()                                       # planar copy          (generic kernel)
+    assert cl.stride(1) == 1 and pl.stride(1) != 1
+    nii = cases.synthetic.default_nifti_affine(B, 2.0).cuda()
+    P = cases.random_pre_affine(B, 58, 0.25).cuda()
+    kw = dict(target_fov_mm=torch.tensor([56.0, 56.0, 2.0]), target_fov_vox=torch.tensor([28, 28, 1]))
+    outs, grads = [], []
+    for v in (cl, pl):
+        v = v.detach().requires_grad_(True)
+        p = P.clone().requires_grad_(True)
+        y, ga, _ = afb.nifti_grid_sample(v, nii, pre_grid_sample_affine=p, **kw)
+        (y.float() * cases.pattern(y.shape, 1.0).cuda()).sum().backward()
+        outs.append(y.detach()); grads.append((v.grad.float().contiguous(), p.grad))
+    assert outs[0].dtype == dt and torch.equal(outs[0], outs[1])
+    close(grads[0][0], grads[1][0], 2e-2 if dt != torch.float32 else 1e-5)      # dVolume is rounded to the storage type
+    close(grads[0][1], grads[1][1], 1e-5)
+    ref, _, _ = O.nifti_grid_sample(pl.float().cpu(), nii.cpu(), pre_grid_sample_affine=P.cpu(), **kw)
+    close(outs[0].float(), ref.to(dt).float(), {torch.float32: 1e-6, torch.bfloat16: 2.0 ** -8, torch.float16: 2.0 ** -10}[dt])
+
+
 def test_channels_last_volume_view(afb):
     """running/run_dl.py:261-264 hands the sampler a channels-last *view* (one_hot + rearrange)."""
     B, S, C = 2, 24, 8
