@@ -459,43 +459,52 @@ def kernel_breakdown(AF, dev, soft, label, image, nii, gpre, params, init, go, f
     del buf
     # min pass
     t = _time(lambda: AF.volume_min(soft, with_mask=True), dev)
-    out["volume_min_mask(soft)"] = {"ms": t, "bytes": soft.numel() * 4 + soft.numel() // 8, "bound": "hbm"}
+    out["volume_min_mask(soft)"] = {"kernel": "volume_min_mask_kernel", "ms": t, "bytes": soft.numel() * 4 + soft.numel() // 8, "bound": "hbm"}
     pad_s, pad_i = AF.volume_min(soft, with_mask=True), AF.volume_min(image)
     spec = AF.ViewSpec(kind=L.AFFINE_PARAMS, V=V, gpre=gpre.reshape(nS, 4, 4).contiguous(), init=init, R=R, spat=S,
                        offset_clip=OFFSET_CLIP, zoom_clip=ZOOM_CLIP, nii_affine=nii, fov_mm=tuple(fov_mm),
                        params=params.detach().reshape(nS, NP).contiguous())
     t = _time(lambda: AF.prepare_views(spec, nv, (S, S, S), fov_vox, dev), dev)
-    out["view_prologue"] = {"ms": t, "bytes": nS * (NP * 4 + 64 + 128), "bound": "latency"}
+    out["view_prologue"] = {"kernel": "view_prologue_kernel", "ms": t, "bytes": nS * (NP * 4 + 64 + 128), "bound": "latency"}
     spec = AF.prepare_views(spec, nv, (S, S, S), fov_vox, dev)[0]
     sd = soft.detach()
     t = _time(lambda: AF._slice_forward_raw(sd, spec, fov_vox, L.BILINEAR, L.PAD_DEVICE, 0.0, pad_s), dev)
-    out["slice_fwd(soft C=8 bilinear)"] = {"ms": t, "bytes": nS * Npix * NUM_CLASSES * 36, "bound": "l2"}
+    out["slice_fwd(soft C=8 bilinear)"] = {"kernel": "slice_fwd_cl_kernel<float, 0>", "ms": t, "bytes": nS * Npix * NUM_CLASSES * 36, "bound": "l2"}
     t = _time(lambda: AF._slice_forward_raw(label, spec, fov_vox, L.NEAREST, L.PAD_ZERO, 0.0, None), dev)
-    out["slice_fwd(label C=8 int64 nearest)"] = {"ms": t, "bytes": nS * Npix * NUM_CLASSES * 16, "bound": "l2"}
+    out["slice_fwd(label C=8 int64 nearest)"] = {"kernel": "slice_fwd_cl_kernel<long, 1>", "ms": t, "bytes": nS * Npix * NUM_CLASSES * 16, "bound": "l2"}
     t = _time(lambda: AF._slice_forward_raw(image, spec, fov_vox, L.BILINEAR, L.PAD_DEVICE, 0.0, pad_i), dev)
-    out["slice_fwd(image C=1 bilinear)"] = {"ms": t, "bytes": nS * Npix * 36, "bound": "l2"}
+    out["slice_fwd(image C=1 bilinear)"] = {"kernel": "slice_fwd_kernel<float, 0>", "ms": t, "bytes": nS * Npix * 36, "bound": "l2"}
     # backward pieces
     d_vol = torch.empty_strided(sd.shape, sd.stride(), dtype=torch.float32, device=dev)
     ws = torch.zeros(int(lib.afb_slice_bwd_workspace_bytes(nS)), dtype=torch.uint8, device=dev)
     d_aff = torch.zeros(nS, NP, device=dev); d_pad = torch.zeros(1, device=dev)
     vd, vs = L.volume_desc(sd), spec.struct()
     t = _time(lambda: L.check(lib.afb_slice_pad_grad(C.byref(vd), C.byref(vs), S, S, 1, L.ptr(go), L.ptr(d_pad), st), "afb_slice_pad_grad"), dev)
-    out["slice_pad_grad"] = {"ms": t, "bytes": nS * Npix * NUM_CLASSES * 4, "bound": "hbm"}
+    out["slice_pad_grad"] = {"kernel": "slice_pad_grad_kernel", "ms": t, "bytes": nS * Npix * NUM_CLASSES * 4, "bound": "hbm"}
     t = _time(lambda: L.check(lib.afb_min_grad_fill_mask(L.ptr(pad_s._afb_mask), sd.numel(), L.ptr(pad_s), L.ptr(d_pad), L.ptr(d_vol), st), "afb_min_grad_fill_mask"), dev)
-    out["min_grad_fill_mask(dVolume)"] = {"ms": t, "bytes": sd.numel() * 4 + sd.numel() // 8, "bound": "hbm"}
+    out["min_grad_fill_mask(dVolume)"] = {"kernel": "min_grad_fill_mask_kernel", "ms": t, "bytes": sd.numel() * 4 + sd.numel() // 8, "bound": "hbm"}
     t = _time(lambda: L.check(lib.afb_min_grad_fill(L.ptr(sd), L.F32, sd.numel(), L.ptr(pad_s), L.ptr(d_pad), L.ptr(d_vol), st), "afb_min_grad_fill"), dev)
-    out["min_grad_fill(dVolume, re-reads the volume) [not in step]"] = {"ms": t, "bytes": sd.numel() * 8, "bound": "hbm"}
+    out["min_grad_fill(dVolume, re-reads the volume) [not in step]"] = {"kernel": "min_grad_fill_kernel<float>", "ms": t, "bytes": sd.numel() * 8, "bound": "hbm"}
 
     def bwd(with_dvol):
         L.check(lib.afb_slice_bwd(C.byref(vd), C.byref(vs), S, S, 1, L.PAD_DEVICE, 0.0, L.ptr(pad_s), L.ptr(go), None,
                                   L.ptr(d_vol) if with_dvol else None, L.ptr(d_aff), None, None, L.ptr(ws), st), "afb_slice_bwd")
     t = _time(lambda: bwd(True), dev)
-    out["slice_bwd(soft, dVolume+dTheta)"] = {"ms": t, "bytes": nS * Npix * NUM_CLASSES * (32 + 4 + 32), "bound": "l2"}
+    out["slice_bwd(soft, dVolume+dTheta)"] = {"kernel": "slice_bwd_cl_kernel<float>", "ms": t, "bytes": nS * Npix * NUM_CLASSES * (32 + 4 + 32), "bound": "l2"}
     t = _time(lambda: bwd(False), dev)
-    out["slice_bwd(soft, dTheta only) [not in step]"] = {"ms": t, "bytes": nS * Npix * NUM_CLASSES * (32 + 4), "bound": "l2"}
+    out["slice_bwd(soft, dTheta only) [not in step]"] = {"kernel": "slice_bwd_cl_kernel<float>", "ms": t, "bytes": nS * Npix * NUM_CLASSES * (32 + 4), "bound": "l2"}
     for k, v in out.items():
         v["gbs"] = v["bytes"] / (v["ms"] * 1e-3) / 1e9
     return out, l2_gbs
+
+
+def ncu_traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel, from the committed `ncu --set full` capture of
+    this same workload (profiles/ncu_traffic.json, written by profiles/ncu_summary.py --traffic); None if not captured."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None
+    return json.load(open(path)).get("kernels", {}).get(kernel_key)
 
 
 def make_roofline(breakdown, l2_gbs):
@@ -511,7 +520,7 @@ def make_roofline(breakdown, l2_gbs):
     for v in breakdown.values():
         v["frac"] = None if v["bound"] == "latency" else v["gbs"] / (hbm if v["bound"] == "hbm" else l2_gbs)
     return {"kernel": name, "bound": k["bound"], "achieved": k["gbs"], "peak": peak, "unit": "GB/s", "frac": k["gbs"] / peak,
-            "traffic": None, "peak_source": src if k["bound"] == "hbm" else "L2 read bandwidth measured in this run: afb_probe_read, 64 passes over a 32 MiB L2-resident buffer in one launch",
+            "traffic": ncu_traffic(k.get("kernel", "")), "cuda_kernel": k.get("kernel"), "peak_source": src if k["bound"] == "hbm" else "L2 read bandwidth measured in this run: afb_probe_read, 64 passes over a 32 MiB L2-resident buffer in one launch",
             "algorithmic_bytes_per_launch": k["bytes"], "ms_per_launch": k["ms"]}
 
 

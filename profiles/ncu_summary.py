@@ -21,9 +21,14 @@ KEYS = {
  'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum': 'ld_sectors', 'l1tex__t_requests_pipe_lsu_mem_global_op_red.sum': 'red_requests',
  'l1tex__t_sectors_pipe_lsu_mem_global_op_red.sum': 'red_sectors', 'launch__grid_size': 'grid', 'launch__block_size': 'block',
 }
+TRAFFIC = '--traffic' in sys.argv
+if TRAFFIC:
+    sys.argv.remove('--traffic')
 out = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 h, units = rows[0], rows[1]
+UNIT = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+traffic = {}
 for r in rows[2:]:
     d = {'kernel': r[h.index('Kernel Name')].split('(')[0][:60]}
     for k, short in KEYS.items():
@@ -35,4 +40,12 @@ for r in rows[2:]:
                 d[short] = r[i]
             if units[i] and short in ('time', 'dram_read', 'dram_write', 'l2_bytes', 'l1_bytes'):
                 d[short + '_unit'] = units[i]
-    print(json.dumps(d))
+    if TRAFFIC:
+        name = d['kernel'].replace('void ', '').replace('afb::', '').strip()
+        tot = d.get('dram_read', 0.0) * UNIT.get(d.get('dram_read_unit', 'byte'), 1.0) + d.get('dram_write', 0.0) * UNIT.get(d.get('dram_write_unit', 'byte'), 1.0)
+        traffic.setdefault(name, []).append(tot)
+    else:
+        print(json.dumps(d))
+if TRAFFIC:
+    print(json.dumps({'source': sys.argv[1], 'what': 'dram__bytes_read.sum + dram__bytes_write.sum per launch (mean over captured launches)',
+                      'kernels': {k: sum(v) / len(v) for k, v in traffic.items()}}, indent=1))
