@@ -50,6 +50,9 @@ _SIGNATURES = {
     "afb_min_mask_bytes": (C.c_int64, [C.c_int64]),
     "afb_volume_min_mask": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "afb_min_grad_fill_mask": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "afb_onehot_expand": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                    C.c_int64, C.c_void_p]),
+    "afb_min_count_from_mask": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "afb_probe_read": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "afb_view_state_bytes": (C.c_int64, []),
     "afb_view_prologue": (C.c_int, [C.POINTER(AfbViews), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

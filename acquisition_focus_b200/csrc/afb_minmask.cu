@@ -31,47 +31,13 @@ __device__ __forceinline__ void mm_merge(float& m, float& n, float m2, float n2)
 
 // mask layout: [n_chunks] float chunk minima, then [n_chunks][32] uint16 (bit 4*j+e of lane l <-> element
 // chunk*512 + j*128 + l*4 + e)
-__global__ void __launch_bounds__(MM_THREADS)
-volume_min_mask_kernel(const float* __restrict__ data, long long n, long long n_chunks, float* __restrict__ chunk_min,
-                       unsigned short* __restrict__ bits, MinCountF* __restrict__ partial, unsigned* __restrict__ counter,
-                       float* __restrict__ out) {
+// CTA reduction of each lane's (min, multiplicity), then the last CTA to arrive reduces the per-CTA partials into out[0..1]
+// and re-arms the counter.  Called by all threads of the CTA.
+__device__ __forceinline__ void mm_finish(float gm, float gc, MinCountF* __restrict__ partial, unsigned* __restrict__ counter,
+                                          float* __restrict__ out) {
     __shared__ float sm[MM_THREADS / 32], sn[MM_THREADS / 32];
     __shared__ bool last;
     const int t = threadIdx.x, w = t >> 5, lane = t & 31;
-    const long long warps = (long long)gridDim.x * (MM_THREADS / 32);
-    float gm = INFINITY, gc = 0.0f;                           // this lane's running (min, multiplicity)
-    for (long long ch = (long long)blockIdx.x * (MM_THREADS / 32) + w; ch < n_chunks; ch += warps) {
-        const long long base = ch * MM_CHUNK;
-        float4 v[MM_LOADS];
-#pragma unroll
-        for (int j = 0; j < MM_LOADS; ++j) {
-            const long long e = base + j * 128 + lane * 4;
-            if (e + 3 < n) {
-                v[j] = __ldcs(reinterpret_cast<const float4*>(data + e));
-            } else {
-                v[j].x = e + 0 < n ? data[e + 0] : INFINITY;
-                v[j].y = e + 1 < n ? data[e + 1] : INFINITY;
-                v[j].z = e + 2 < n ? data[e + 2] : INFINITY;
-                v[j].w = INFINITY;
-            }
-        }
-        float c = INFINITY;
-#pragma unroll
-        for (int j = 0; j < MM_LOADS; ++j) c = fminf(fminf(fminf(c, v[j].x), fminf(v[j].y, v[j].z)), v[j].w);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c = fminf(c, __shfl_xor_sync(0xffffffffu, c, o));
-        unsigned b = 0u;
-#pragma unroll
-        for (int j = 0; j < MM_LOADS; ++j) {
-            const unsigned q = (v[j].x == c ? 1u : 0u) | (v[j].y == c ? 2u : 0u) | (v[j].z == c ? 4u : 0u) | (v[j].w == c ? 8u : 0u);
-            b |= q << (4 * j);
-        }
-        bits[ch * 32 + lane] = (unsigned short)b;
-        if (lane == 0) chunk_min[ch] = c;
-        // chunk minimum with this lane's share of its multiplicity (lanes that do not attain c contribute 0)
-        mm_merge(gm, gc, c, (float)__popc(b));
-    }
-    // CTA reduction of (min, multiplicity), then the last CTA reduces the per-CTA partials
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const float m2 = __shfl_xor_sync(0xffffffffu, gm, o), n2 = __shfl_xor_sync(0xffffffffu, gc, o);
@@ -110,25 +76,90 @@ volume_min_mask_kernel(const float* __restrict__ data, long long n, long long n_
     }
 }
 
-// d_vol = (vol == min) ? d_pad / count : 0 from the chunk record (never touches the volume)
+__device__ __forceinline__ void mm_load_chunk(const float* __restrict__ data, long long n, long long ch, int lane, float4* v) {
+    const long long base = ch * MM_CHUNK;
+#pragma unroll
+    for (int j = 0; j < MM_LOADS; ++j) {
+        const long long e = base + j * 128 + lane * 4;
+        if (e + 3 < n) {
+            v[j] = __ldcs(reinterpret_cast<const float4*>(data + e));
+        } else {
+            v[j].x = e + 0 < n ? data[e + 0] : INFINITY;
+            v[j].y = e + 1 < n ? data[e + 1] : INFINITY;
+            v[j].z = e + 2 < n ? data[e + 2] : INFINITY;
+            v[j].w = INFINITY;
+        }
+    }
+}
+
+// A register double buffer (next chunk requested before the current one is reduced) was measured SLOWER on the
+// B200 (0.740 vs 0.719 ms per 4.3 GB: 63 registers cost two resident CTAs per SM), as was sizing the grid to exactly
+// one resident wave (0.731): the plain loop below at 148 x 8 CTAs reads at 6.1-6.2 TB/s.
+__global__ void __launch_bounds__(MM_THREADS)
+volume_min_mask_kernel(const float* __restrict__ data, long long n, long long n_chunks, float* __restrict__ chunk_min,
+                       unsigned short* __restrict__ bits, MinCountF* __restrict__ partial, unsigned* __restrict__ counter,
+                       float* __restrict__ out) {
+    const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+    const long long warps = (long long)gridDim.x * (MM_THREADS / 32);
+    float gm = INFINITY, gc = 0.0f;                           // this lane's running (min, multiplicity)
+    for (long long ch = (long long)blockIdx.x * (MM_THREADS / 32) + w; ch < n_chunks; ch += warps) {
+        float4 v[MM_LOADS];
+        mm_load_chunk(data, n, ch, lane, v);
+        float c = INFINITY;
+#pragma unroll
+        for (int j = 0; j < MM_LOADS; ++j) c = fminf(fminf(fminf(c, v[j].x), fminf(v[j].y, v[j].z)), v[j].w);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c = fminf(c, __shfl_xor_sync(0xffffffffu, c, o));
+        unsigned b = 0u;
+#pragma unroll
+        for (int j = 0; j < MM_LOADS; ++j) {
+            const unsigned q = (v[j].x == c ? 1u : 0u) | (v[j].y == c ? 2u : 0u) | (v[j].z == c ? 4u : 0u) | (v[j].w == c ? 8u : 0u);
+            b |= q << (4 * j);
+        }
+        bits[ch * 32 + lane] = (unsigned short)b;
+        if (lane == 0) chunk_min[ch] = c;
+        // chunk minimum with this lane's share of its multiplicity (lanes that do not attain c contribute 0)
+        mm_merge(gm, gc, c, (float)__popc(b));
+    }
+    mm_finish(gm, gc, partial, counter, out);
+}
+
+// d_vol = (vol == min) ? d_pad / count : 0 from the chunk record (never touches the volume).
+// Loop-free: one warp per group of G consecutive chunks, the group's records (chunk minima + bit words, independent
+// loads) fetched up front, then G x 2 KiB of 16-byte stores.  Measured on the B200 over 4.3 GB of dVolume: the earlier
+// persistent grid-stride loop (record load -> stores chained in every iteration) 0.790 ms; loop-free G = 8 / 4 / 2 / 1:
+// 0.688 / 0.690 / 0.670 / 0.665 ms (6.7 TB/s; torch's plain zero_() of the same tensor: 0.578 ms).
+constexpr int MM_GROUP = 1;
+
+template <int G>
 __global__ void __launch_bounds__(MM_THREADS)
 min_grad_fill_mask_kernel(const float* __restrict__ chunk_min, const unsigned short* __restrict__ bits, long long n,
                           long long n_chunks, const float* __restrict__ min_count, const float* __restrict__ d_pad,
                           float* __restrict__ d_vol) {
-    const float m = __ldg(min_count), share = __ldg(d_pad) / __ldg(min_count + 1);
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long warps = (long long)gridDim.x * (MM_THREADS / 32);
-    for (long long ch = (long long)blockIdx.x * (MM_THREADS / 32) + w; ch < n_chunks; ch += warps) {
-        const bool hot = __ldg(chunk_min + ch) == m;
-        const unsigned b = hot ? (unsigned)__ldg(bits + ch * 32 + lane) : 0u;
-        const long long base = ch * MM_CHUNK;
+    const long long ch0 = ((long long)blockIdx.x * (MM_THREADS / 32) + w) * G;
+    if (ch0 >= n_chunks) return;
+    float cm[G];
+    unsigned braw[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const bool ok = ch0 + g < n_chunks;
+        cm[g] = ok ? __ldg(chunk_min + ch0 + g) : INFINITY;
+        braw[g] = ok ? (unsigned)__ldg(bits + (ch0 + g) * 32 + lane) : 0u;
+    }
+    const float m = __ldg(min_count), share = __ldg(d_pad) / __ldg(min_count + 1);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        if (ch0 + g >= n_chunks) break;
+        const unsigned b = cm[g] == m ? braw[g] : 0u;
+        const long long base = (ch0 + g) * MM_CHUNK;
 #pragma unroll
         for (int j = 0; j < MM_LOADS; ++j) {
             const long long e = base + j * 128 + lane * 4;
             const unsigned q = (b >> (4 * j)) & 15u;
             const float4 o = make_float4((q & 1u) ? share : 0.0f, (q & 2u) ? share : 0.0f, (q & 4u) ? share : 0.0f, (q & 8u) ? share : 0.0f);
             if (e + 3 < n) {
-                __stcs(reinterpret_cast<float4*>(d_vol + e), o);
+                *reinterpret_cast<float4*>(d_vol + e) = o;
             } else {
                 if (e + 0 < n) d_vol[e + 0] = o.x;
                 if (e + 1 < n) d_vol[e + 1] = o.y;
@@ -136,6 +167,99 @@ min_grad_fill_mask_kernel(const float* __restrict__ chunk_min, const unsigned sh
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// One-hot materialisation of running/run_dl.py:261-264 fused with the min record.
+//   label map (integer, one value per voxel) -> int64 one-hot [voxel][C] and/or fp32 one-hot [voxel][C]
+//   (channels-last in memory, i.e. exactly the strides of `one_hot(lab).permute(0,4,1,2,3)` and of its `.float()`).
+// While the fp32 values are in registers the kernel also writes their chunk record (chunk minimum + "== minimum" bits,
+// same layout as volume_min_mask_kernel), so the separate 4 B/voxel min pass over the soft-label volume disappears for
+// volumes that are produced here.  Works on a RANGE of a larger tensor (labels / outputs point at the range, chunk0 is
+// the range's first chunk in the whole tensor's record) so that a host batch can be expanded chunk by chunk while the next chunk is still in flight
+// over PCIe; afb_min_count_from_mask then reduces the whole record to (min, multiplicity).
+// Labels outside [0, C) give an all-zero voxel (torch's one_hot raises instead).
+// ------------------------------------------------------------------------------------------------
+template <typename TL>
+__global__ void __launch_bounds__(MM_THREADS)
+onehot_expand_kernel(const TL* __restrict__ labels, long long n_elem, int C, long long chunk0,
+                     long long* __restrict__ onehot, float* __restrict__ soft, float* __restrict__ chunk_min,
+                     unsigned short* __restrict__ bits) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long lc = (long long)blockIdx.x * (MM_THREADS / 32) + w;       // chunk within the range
+    const long long base = lc * MM_CHUNK;                                      // first element of the chunk within the range
+    if (base >= n_elem) return;
+    const bool pow2 = (C & (C - 1)) == 0;
+    const int shift = 31 - __clz(C);
+    auto value_at = [&](long long e) -> int {                                  // one-hot value of range element e
+        const long long vox = pow2 ? (e >> shift) : (e / C);
+        const int ch = (int)(pow2 ? (e & (C - 1)) : (e - vox * C));
+        return (long long)__ldg(labels + vox) == (long long)ch ? 1 : 0;
+    };
+    float4 v[MM_LOADS];
+#pragma unroll
+    for (int j = 0; j < MM_LOADS; ++j) {
+        const long long e = base + j * 128 + lane * 4;
+        v[j].x = e + 0 < n_elem ? (float)value_at(e + 0) : INFINITY;
+        v[j].y = e + 1 < n_elem ? (float)value_at(e + 1) : INFINITY;
+        v[j].z = e + 2 < n_elem ? (float)value_at(e + 2) : INFINITY;
+        v[j].w = e + 3 < n_elem ? (float)value_at(e + 3) : INFINITY;
+    }
+    if (soft) {
+#pragma unroll
+        for (int j = 0; j < MM_LOADS; ++j) {
+            const long long e = base + j * 128 + lane * 4;
+            if (e + 3 < n_elem) {
+                *reinterpret_cast<float4*>(soft + e) = v[j];
+            } else {
+                if (e + 0 < n_elem) soft[e + 0] = v[j].x;
+                if (e + 1 < n_elem) soft[e + 1] = v[j].y;
+                if (e + 2 < n_elem) soft[e + 2] = v[j].z;
+            }
+        }
+    }
+    if (chunk_min) {
+        float c = INFINITY;
+#pragma unroll
+        for (int j = 0; j < MM_LOADS; ++j) c = fminf(fminf(fminf(c, v[j].x), fminf(v[j].y, v[j].z)), v[j].w);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c = fminf(c, __shfl_xor_sync(0xffffffffu, c, o));
+        unsigned b = 0u;
+#pragma unroll
+        for (int j = 0; j < MM_LOADS; ++j) {
+            const unsigned q = (v[j].x == c ? 1u : 0u) | (v[j].y == c ? 2u : 0u) | (v[j].z == c ? 4u : 0u) | (v[j].w == c ? 8u : 0u);
+            b |= q << (4 * j);
+        }
+        const long long gch = chunk0 + lc;
+        bits[gch * 32 + lane] = (unsigned short)b;
+        if (lane == 0) chunk_min[gch] = c;
+    }
+    if (onehot) {
+        // int64 output: 16-byte pieces laid out so that every store instruction of the warp covers 512 contiguous bytes
+#pragma unroll
+        for (int k = 0; k < 2 * MM_LOADS; ++k) {
+            const long long e = base + ((long long)k * 32 + lane) * 2;
+            if (e + 1 < n_elem) {
+                longlong2 o;
+                o.x = value_at(e); o.y = value_at(e + 1);
+                *reinterpret_cast<longlong2*>(onehot + e) = o;
+            } else if (e < n_elem) {
+                onehot[e] = value_at(e);
+            }
+        }
+    }
+}
+
+// (min, multiplicity) of a whole tensor from its chunk record alone (4.1 % of the tensor's bytes)
+__global__ void __launch_bounds__(MM_THREADS)
+mask_reduce_kernel(const float* __restrict__ chunk_min, const unsigned short* __restrict__ bits, long long n_chunks,
+                   MinCountF* __restrict__ partial, unsigned* __restrict__ counter, float* __restrict__ out) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long warps = (long long)gridDim.x * (MM_THREADS / 32);
+    float gm = INFINITY, gc = 0.0f;
+    for (long long ch = (long long)blockIdx.x * (MM_THREADS / 32) + w; ch < n_chunks; ch += warps)
+        mm_merge(gm, gc, __ldg(chunk_min + ch), (float)__popc((unsigned)__ldg(bits + ch * 32 + lane)));
+    mm_finish(gm, gc, partial, counter, out);
 }
 
 }  // namespace afb
@@ -172,8 +296,60 @@ extern "C" int afb_min_grad_fill_mask(const void* mask, int64_t n, const float* 
     const long long c = mm_chunks(n);
     const float* chunk_min = (const float*)mask;
     const unsigned short* bits = (const unsigned short*)((const char*)mask + ((c * (long long)sizeof(float) + 15) / 16) * 16);
+    const long long per_cta = (long long)(MM_THREADS / 32) * MM_GROUP;
+    const long long blocks = (c + per_cta - 1) / per_cta;
+    if (blocks > 2147483647ll) return AFB_EUNSUPPORTED;
+    min_grad_fill_mask_kernel<MM_GROUP><<<(unsigned)blocks, MM_THREADS, 0, (cudaStream_t)stream>>>(chunk_min, bits, n, c, min_count,
+                                                                                                  d_pad, d_vol);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int afb_onehot_expand(const void* labels, int label_dtype, int64_t n_voxels, int num_classes, int64_t* onehot_i64,
+                                 float* soft_f32, void* mask, int64_t total_elements, int64_t elem_offset, void* stream) {
+    if (!labels || n_voxels <= 0 || num_classes <= 0 || (!onehot_i64 && !soft_f32)) return AFB_EINVAL;
+    if (((uintptr_t)onehot_i64 & 15u) || ((uintptr_t)soft_f32 & 15u) || ((uintptr_t)mask & 15u)) return AFB_EINVAL;
+    const long long n_elem = (long long)n_voxels * num_classes;
+    float* chunk_min = nullptr;
+    unsigned short* bits = nullptr;
+    long long chunk0 = 0;
+    if (mask) {
+        if (!soft_f32 || elem_offset < 0 || elem_offset % MM_CHUNK != 0 || elem_offset + n_elem > total_elements) return AFB_EINVAL;
+        // a range that does not end the tensor must end on a chunk boundary, or its last chunk's record would be partial
+        if (elem_offset + n_elem != total_elements && n_elem % MM_CHUNK != 0) return AFB_EINVAL;
+        const long long c = mm_chunks(total_elements);
+        chunk_min = (float*)mask;
+        bits = (unsigned short*)((char*)mask + ((c * (long long)sizeof(float) + 15) / 16) * 16);
+        chunk0 = elem_offset / MM_CHUNK;
+    }
+    const long long chunks = mm_chunks(n_elem);
+    const long long blocks = (chunks + MM_THREADS / 32 - 1) / (MM_THREADS / 32);
+    if (blocks > 2147483647ll) return AFB_EUNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+#define AFB_EXP(TL) onehot_expand_kernel<TL><<<(unsigned)blocks, MM_THREADS, 0, st>>>((const TL*)labels, n_elem, num_classes, \
+        chunk0, (long long*)onehot_i64, soft_f32, chunk_min, bits)
+    switch (label_dtype) {
+        case AFB_I64: AFB_EXP(int64_t); break;
+        case AFB_I32: AFB_EXP(int32_t); break;
+        case AFB_I16: AFB_EXP(int16_t); break;
+        case AFB_U8: AFB_EXP(uint8_t); break;
+        default: return AFB_EDTYPE;
+    }
+#undef AFB_EXP
+    return (int)cudaGetLastError();
+}
+
+extern "C" int afb_min_count_from_mask(const void* mask, int64_t n, float* out_min_count, void* workspace, void* stream) {
+    if (!mask || !out_min_count || !workspace || n <= 0 || ((uintptr_t)mask & 15u)) return AFB_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long c = mm_chunks(n);
+    const float* chunk_min = (const float*)mask;
+    const unsigned short* bits = (const unsigned short*)((const char*)mask + ((c * (long long)sizeof(float) + 15) / 16) * 16);
+    unsigned* counter = (unsigned*)workspace;
+    MinCountF* partial = (MinCountF*)((char*)workspace + 16);
+    cudaError_t e = cudaMemsetAsync(counter, 0, 16, st);
+    if (e != cudaSuccess) return (int)e;
     const long long wantb = (c + MM_THREADS / 32 - 1) / (MM_THREADS / 32);
-    const int blocks = (int)(wantb < 148 * 16 ? wantb : 148 * 16);
-    min_grad_fill_mask_kernel<<<blocks, MM_THREADS, 0, (cudaStream_t)stream>>>(chunk_min, bits, n, c, min_count, d_pad, d_vol);
+    const int blocks = (int)(wantb < MM_BLOCKS ? wantb : MM_BLOCKS);
+    mask_reduce_kernel<<<blocks, MM_THREADS, 0, st>>>(chunk_min, bits, c, partial, counter, out_min_count);
     return (int)cudaGetLastError();
 }

@@ -26,12 +26,12 @@ struct Pix {
     bool valid;
 };
 
-__device__ __forceinline__ Pix pixel_of_thread(const OutGeom& g) {
+__device__ __forceinline__ Pix pixel_of_tile(const OutGeom& g, int tile) {
     const int tid = threadIdx.x;
     const int w = tid >> 5, lane = tid & 31;
     const int lc = ((w & 1) << 3) + (lane & 7);
     const int lr = ((w >> 1) << 2) + (lane >> 3);
-    const int tr = blockIdx.x / g.tiles_c, tc = blockIdx.x % g.tiles_c;
+    const int tr = tile / g.tiles_c, tc = tile % g.tiles_c;
     const int row = tr * TILE + lr, col = tc * TILE + lc;
     Pix p;
     p.valid = row < g.rows && col < g.cols;
@@ -42,6 +42,8 @@ __device__ __forceinline__ Pix pixel_of_thread(const OutGeom& g) {
     }
     return p;
 }
+
+__device__ __forceinline__ Pix pixel_of_thread(const OutGeom& g) { return pixel_of_tile(g, blockIdx.x); }
 
 struct Sample {                 // un-normalised source coordinates of one output location
     float ix, iy, iz;
@@ -64,38 +66,58 @@ __device__ __forceinline__ Sample sample_coords(const OutGeom& g, const Pix& p, 
     return sm;
 }
 
-// 16-byte channel vectors of the channels-last kernels: how many elements, and how to widen them to fp32
-template <typename T> struct Vec16 {
-    static constexpr int N = 16 / (int)sizeof(T);
-    static constexpr bool is_float = false;
-};
-template <> struct Vec16<float> {
-    static constexpr int N = 4;
+// Channel vectors of the channels-last kernels.  One gather moves VB = 16 or 32 bytes of a voxel's contiguous channels:
+// sm_100 has 256-bit global loads (ld.global.nc.v8.b32 -> LDG.E.256), so the 8 fp32 channels of a one-hot corner
+// (exactly one 32-byte L2 sector) are ONE load instruction instead of two - half the LSU instructions and half the
+// per-instruction line replays of an L1-wavefront-bound gather.
+template <int VB> struct Raw { unsigned w[VB / 4]; };
+
+template <int VB> __device__ __forceinline__ Raw<VB> gather_nc(const void* p);
+template <> __device__ __forceinline__ Raw<16> gather_nc<16>(const void* p) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    Raw<16> r;
+    r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
+    return r;
+}
+template <> __device__ __forceinline__ Raw<32> gather_nc<32>(const void* p) {     // p must be 32-byte aligned
+    Raw<32> r;
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+        : "l"(p));
+    return r;
+}
+template <int VB> __device__ __forceinline__ Raw<VB> raw_zero() {
+    Raw<VB> r;
+#pragma unroll
+    for (int i = 0; i < VB / 4; ++i) r.w[i] = 0u;
+    return r;
+}
+
+// how the storage type widens to fp32, per 32-bit word of a gathered vector
+template <typename T> struct Widen { static constexpr bool is_float = false; };
+template <> struct Widen<float> {
     static constexpr bool is_float = true;
-    static __device__ __forceinline__ void decode(const uint4& r, float* o) {
-        o[0] = __uint_as_float(r.x); o[1] = __uint_as_float(r.y); o[2] = __uint_as_float(r.z); o[3] = __uint_as_float(r.w);
+    template <int VB> static __device__ __forceinline__ void decode(const Raw<VB>& r, float* o) {
+#pragma unroll
+        for (int i = 0; i < VB / 4; ++i) o[i] = __uint_as_float(r.w[i]);
     }
 };
-template <> struct Vec16<__nv_bfloat16> {
-    static constexpr int N = 8;
+template <> struct Widen<__nv_bfloat16> {
     static constexpr bool is_float = true;
-    static __device__ __forceinline__ void decode(const uint4& r, float* o) {
-        const unsigned w[4] = {r.x, r.y, r.z, r.w};
+    template <int VB> static __device__ __forceinline__ void decode(const Raw<VB>& r, float* o) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {           // bf16 -> fp32 is a 16-bit shift
-            o[2 * i] = __uint_as_float(w[i] << 16);
-            o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        for (int i = 0; i < VB / 4; ++i) {      // bf16 -> fp32 is a 16-bit shift
+            o[2 * i] = __uint_as_float(r.w[i] << 16);
+            o[2 * i + 1] = __uint_as_float(r.w[i] & 0xffff0000u);
         }
     }
 };
-template <> struct Vec16<__half> {
-    static constexpr int N = 8;
+template <> struct Widen<__half> {
     static constexpr bool is_float = true;
-    static __device__ __forceinline__ void decode(const uint4& r, float* o) {
-        const __half2* h = reinterpret_cast<const __half2*>(&r);
+    template <int VB> static __device__ __forceinline__ void decode(const Raw<VB>& r, float* o) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float2 f = __half22float2(h[i]);
+        for (int i = 0; i < VB / 4; ++i) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&r.w[i]));
             o[2 * i] = f.x; o[2 * i + 1] = f.y;
         }
     }

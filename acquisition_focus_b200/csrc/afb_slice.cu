@@ -66,10 +66,10 @@ slice_fwd_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad_va
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward, channels-last volumes: 16-byte vector gathers.  Arithmetic per channel is identical to the
-// generic kernel (bitwise the same results).
+// forward, channels-last volumes: VB-byte vector gathers (VB = 32: one LDG.256 per corner of an 8-channel fp32
+// voxel; VB = 16: LDG.128).  Arithmetic per channel is identical to the generic kernel (bitwise the same results).
 // ------------------------------------------------------------------------------------------------
-template <typename T, int MODE>
+template <typename T, int MODE, int VB, int BATCH = 8>
 __global__ void __launch_bounds__(NTHREADS, 3)
 slice_fwd_cl_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad_value, const float* pad_device,
                     T* __restrict__ out) {
@@ -81,42 +81,47 @@ slice_fwd_cl_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad
     const T* __restrict__ src = (const T*)vol.data + (long long)b * vol.sB;
     const size_t plane = (size_t)g.Do * g.Ho * g.Wo;
     T* __restrict__ dst = out + (size_t)s * vol.C * plane + ((size_t)p.i * g.Ho + p.j) * g.Wo + p.k;
-    constexpr int N = Vec16<T>::N;
+    constexpr int N = VB / (int)sizeof(T);
 
     if (MODE == AFB_NEAREST) {
         const int xn = __float2int_rn(sm.ix), yn = __float2int_rn(sm.iy), zn = __float2int_rn(sm.iz);
         const bool in = xn >= 0 && xn < vol.W && yn >= 0 && yn < vol.H && zn >= 0 && zn < vol.D;
         const int off = in ? (zn * (int)vol.sD + yn * (int)vol.sH + xn * (int)vol.sW) : 0;
         for (int c0 = 0; c0 < vol.C; c0 += N) {
-            uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-            if (in) raw = __ldg(reinterpret_cast<const uint4*>(src + off + c0));
-            const T* e = reinterpret_cast<const T*>(&raw);
+            Raw<VB> raw = raw_zero<VB>();
+            if (in) raw = gather_nc<VB>(src + off + c0);
+            const T* e = reinterpret_cast<const T*>(raw.w);
 #pragma unroll
             for (int q = 0; q < N; ++q) dst[(size_t)(c0 + q) * plane] = e[q];
         }
         return;
     }
-    if constexpr (Vec16<T>::is_float && MODE == AFB_BILINEAR) {
-        // fp32: 4 channels per 16-byte load; bf16 / fp16 storage: 8 (fp32 coordinates, weights and accumulation)
+    if constexpr (Widen<T>::is_float && MODE == AFB_BILINEAR) {
+        // fp32 coordinates, weights and accumulation whatever the storage type
         const Corners cn = corners_of(sm, vol);
         const float pad = pad_of(pad_mode, pad_value, pad_device);
         for (int c0 = 0; c0 < vol.C; c0 += N) {
-            uint4 raw[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                raw[k] = cn.in(k) ? __ldg(reinterpret_cast<const uint4*>(src + cn.off(k, vol) + c0)) : make_uint4(0u, 0u, 0u, 0u);
             float acc[N];
 #pragma unroll
             for (int q = 0; q < N; ++q) acc[q] = 0.0f;
+            // BATCH corners gathered at a time (8: all in flight; 4: z0 plane then z1 plane, half the registers);
+            // the accumulation order k = 0..7 (ATen's) is the same either way
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (cn.in(k)) {
-                    float vv[N];
-                    Vec16<T>::decode(raw[k], vv);
-                    const float wk = cn.w(k);
+            for (int h = 0; h < 8; h += BATCH) {
+                Raw<VB> raw[BATCH];
 #pragma unroll
-                    for (int q = 0; q < N; ++q) acc[q] = __fadd_rn(acc[q], __fmul_rn(__fsub_rn(vv[q], pad), wk));
-                }
+                for (int k = 0; k < BATCH; ++k)
+                    raw[k] = cn.in(h + k) ? gather_nc<VB>(src + cn.off(h + k, vol) + c0) : raw_zero<VB>();
+#pragma unroll
+                for (int k = 0; k < BATCH; ++k)
+                    if (cn.in(h + k)) {
+                        float vv[N];
+                        Widen<T>::template decode<VB>(raw[k], vv);
+                        const float wk = cn.w(h + k);
+#pragma unroll
+                        for (int q = 0; q < N; ++q) acc[q] = __fadd_rn(acc[q], __fmul_rn(__fsub_rn(vv[q], pad), wk));
+                    }
+            }
 #pragma unroll
             for (int q = 0; q < N; ++q) dst[(size_t)(c0 + q) * plane] = Store<T>::from_float(__fadd_rn(acc[q], pad));
         }
@@ -170,13 +175,14 @@ slice_bwd_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad_va
     bwd_reduce(s, part, pad_mode, d_pad, ws_acc);
 }
 
-// channels-last fp32 volumes: 16-byte gathers and 16-byte vector reductions (red.global.add.v4.f32)
-template <typename T>
+// channels-last volumes: VB-byte gathers (LDG.256 for 8 fp32 channels) and 16-byte vector reductions
+// (red.global.add.v4.f32 - the widest vector RED sm_100 has)
+template <typename T, int VB, int BATCH>
 __global__ void __launch_bounds__(NTHREADS, 2)
 slice_bwd_cl_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad_value, const float* pad_device,
                     const float* __restrict__ grad_out, float* __restrict__ d_vol, float* __restrict__ d_pad,
                     double* __restrict__ ws_acc) {
-    constexpr int N = Vec16<T>::N;
+    constexpr int N = VB / (int)sizeof(T);
     const int s = blockIdx.y;
     float part[13];
 #pragma unroll
@@ -199,23 +205,27 @@ slice_bwd_cl_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad
             float go[N];
 #pragma unroll
             for (int q = 0; q < N; ++q) { go[q] = __ldg(go_p + (size_t)(c0 + q) * plane); gsum += go[q]; }
-            uint4 raw[8];
+            // two batches of 4 corners (z0 plane, z1 plane): 4 vector gathers in flight per thread, half the registers
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                raw[k] = cn.in(k) ? __ldg(reinterpret_cast<const uint4*>(src + cn.off(k, vol) + c0)) : make_uint4(0u, 0u, 0u, 0u);
+            for (int h = 0; h < 8; h += BATCH) {
+                Raw<VB> raw[BATCH];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                if (cn.in(k)) {
-                    float vv[N];
-                    Vec16<T>::decode(raw[k], vv);
+                for (int k = 0; k < BATCH; ++k)
+                    raw[k] = cn.in(h + k) ? gather_nc<VB>(src + cn.off(h + k, vol) + c0) : raw_zero<VB>();
 #pragma unroll
-                    for (int q = 0; q < N; ++q) dot[k] = fmaf(vv[q] - pad, go[q], dot[k]);
-                    if (dv) {
-                        const float wk = cn.w(k);
+                for (int k = 0; k < BATCH; ++k) {
+                    if (cn.in(h + k)) {
+                        float vv[N];
+                        Widen<T>::template decode<VB>(raw[k], vv);
 #pragma unroll
-                        for (int q = 0; q < N; q += 4)
-                            atomicAdd(reinterpret_cast<float4*>(dv + cn.off(k, vol) + c0 + q),
-                                      make_float4(wk * go[q], wk * go[q + 1], wk * go[q + 2], wk * go[q + 3]));
+                        for (int q = 0; q < N; ++q) dot[h + k] = fmaf(vv[q] - pad, go[q], dot[h + k]);
+                        if (dv) {
+                            const float wk = cn.w(h + k);
+#pragma unroll
+                            for (int q = 0; q < N; q += 4)
+                                atomicAdd(reinterpret_cast<float4*>(dv + cn.off(h + k, vol) + c0 + q),
+                                          make_float4(wk * go[q], wk * go[q + 1], wk * go[q + 2], wk * go[q + 3]));
+                        }
                     }
                 }
             }
@@ -227,23 +237,60 @@ slice_bwd_cl_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad
 
 // d(out)/d(pad) = sum go * (1 - sum of in-bounds weights): depends on geometry and grad_out only, so it can run
 // BEFORE the dVolume fill, which lets MinBackward be fused with the zero-fill (afb_min_grad_fill).
+// A pure stream over grad_out: each CTA covers PAD_TILES tiles with all their loads independent (enough bytes in
+// flight to reach HBM speed) and issues one atomic for all of them.
+constexpr int PAD_TILES = 4;
+
 __global__ void __launch_bounds__(NTHREADS, 4)
-slice_pad_grad_kernel(VolArgs vol, ViewArgs va, OutGeom g, const float* __restrict__ grad_out, float* __restrict__ d_pad) {
+slice_pad_grad_kernel(VolArgs vol, ViewArgs va, OutGeom g, int ntiles, const float* __restrict__ grad_out,
+                      float* __restrict__ d_pad) {
     __shared__ float red[NTHREADS / 32];
     const int s = blockIdx.y;
-    const Pix p = pixel_of_thread(g);
+    const size_t plane = (size_t)g.Do * g.Ho * g.Wo;
+    const float* __restrict__ go_s = grad_out + (size_t)s * vol.C * plane;
+    // phase 1: request every grad_out element of the PAD_TILES tiles (predicated, no control flow between the loads)
+    Pix px[PAD_TILES];
+    float gsum[PAD_TILES];
+    if (vol.C == 8) {
+        float v[PAD_TILES][8];
+#pragma unroll
+        for (int u = 0; u < PAD_TILES; ++u) {
+            const int tile = blockIdx.x * PAD_TILES + u;
+            px[u] = pixel_of_tile(g, tile < ntiles ? tile : 0);
+            px[u].valid = px[u].valid && tile < ntiles;
+            const float* __restrict__ go_p = go_s + ((size_t)px[u].i * g.Ho + px[u].j) * g.Wo + px[u].k;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) v[u][c] = px[u].valid ? __ldg(go_p + (size_t)c * plane) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < PAD_TILES; ++u) {
+            gsum[u] = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) gsum[u] += v[u][c];
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < PAD_TILES; ++u) {
+            const int tile = blockIdx.x * PAD_TILES + u;
+            px[u] = pixel_of_tile(g, tile < ntiles ? tile : 0);
+            px[u].valid = px[u].valid && tile < ntiles;
+            const float* __restrict__ go_p = go_s + ((size_t)px[u].i * g.Ho + px[u].j) * g.Wo + px[u].k;
+            gsum[u] = 0.0f;
+            if (px[u].valid)
+                for (int c = 0; c < vol.C; ++c) gsum[u] += __ldg(go_p + (size_t)c * plane);
+        }
+    }
+    // phase 2: geometry (no memory traffic besides the 12 floats of the slice's grid affine)
     float part = 0.0f;
-    if (p.valid) {
-        const Sample sm = sample_coords(g, p, va, s, vol);
+#pragma unroll
+    for (int u = 0; u < PAD_TILES; ++u) {
+        if (!px[u].valid) continue;
+        const Sample sm = sample_coords(g, px[u], va, s, vol);
         const Corners cn = corners_of(sm, vol);
         float wsum = 0.0f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) wsum += cn.in(k) ? cn.w(k) : 0.0f;
-        const size_t plane = (size_t)g.Do * g.Ho * g.Wo;
-        const float* __restrict__ go_p = grad_out + (size_t)s * vol.C * plane + ((size_t)p.i * g.Ho + p.j) * g.Wo + p.k;
-        float gsum = 0.0f;
-        for (int c = 0; c < vol.C; ++c) gsum += __ldg(go_p + (size_t)c * plane);
-        part = gsum * (1.0f - wsum);
+        part += gsum[u] * (1.0f - wsum);
     }
     part = warp_sum(part);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
@@ -270,30 +317,55 @@ static int make_args(const afb_volume* vol, const afb_views* views, int Do, int 
     return make_view_args(views, vol->B, vol->D, vol->H, vol->W, Do, Ho, Wo, /*need_state=*/true, a);
 }
 
-// channels-last fast path: channels contiguous, everything 16-byte aligned
-static bool channels_last_ok(const afb_volume* vol, int n, const void* extra_ptr) {
-    if (vol->sC != 1 || vol->C % n != 0) return false;
-    if (((uintptr_t)vol->data & 15u) || ((uintptr_t)extra_ptr & 15u)) return false;
-    if (vol->sW % n || vol->sH % n || vol->sD % n || vol->sB % n) return false;
-    return true;
+// channels-last fast path: channels contiguous, every voxel's channel vector VB-byte aligned (n = VB / sizeof(T)
+// elements, at most 8 per vector).  Returns the widest usable vector width in bytes (<= max_vb) or 0.
+static int channels_last_vec(const afb_volume* vol, int elem_bytes, const void* extra_ptr, int max_vb) {
+    if (vol->sC != 1) return 0;
+    for (int vb = max_vb; vb >= 16; vb >>= 1) {
+        const int n = vb / elem_bytes;
+        if (n < 1 || n > 8 || vol->C % n != 0) continue;
+        if (((uintptr_t)vol->data % vb) || ((uintptr_t)extra_ptr % 16)) continue;
+        if (vol->sW % n || vol->sH % n || vol->sD % n || vol->sB % n) continue;
+        return vb;
+    }
+    return 0;
 }
 
+// Forward gathers stay at 16 bytes (LDG.128): measured on the B200, one LDG.256 per corner is SLOWER in the forward
+// (0.340 vs 0.303 ms soft labels, 0.245 vs 0.217 ms int64 labels at 384 slices) - the kernel is bound by DRAM-miss
+// latency x loads in flight, and the wider vectors cost a resident CTA per SM.  The backward keeps LDG.256.
 template <typename T>
 static int launch_fwd(const afb_volume* vol, const VolArgs& v, const ViewArgs& a, const OutGeom& g, int mode, int pad_mode,
                       float pad_value, const float* pad_device, void* out, cudaStream_t st) {
     const int S = v.B * a.V;
     const dim3 grid = slice_grid(g, S);
-    const bool cl = channels_last_ok(vol, Vec16<T>::N, nullptr) && (mode == AFB_NEAREST || Vec16<T>::is_float);
-    if (cl) {
-        if (mode == AFB_NEAREST)
-            slice_fwd_cl_kernel<T, AFB_NEAREST><<<grid, NTHREADS, 0, st>>>(v, a, g, pad_mode, pad_value, pad_device, (T*)out);
-        else
-            slice_fwd_cl_kernel<T, AFB_BILINEAR><<<grid, NTHREADS, 0, st>>>(v, a, g, pad_mode, pad_value, pad_device, (T*)out);
+    const int vb = (mode == AFB_NEAREST || Widen<T>::is_float) ? channels_last_vec(vol, (int)sizeof(T), nullptr, 16) : 0;
+    if (vb == 16 && mode == AFB_NEAREST) {
+        slice_fwd_cl_kernel<T, AFB_NEAREST, 16><<<grid, NTHREADS, 0, st>>>(v, a, g, pad_mode, pad_value, pad_device, (T*)out);
+    } else if (vb == 16) {
+        slice_fwd_cl_kernel<T, AFB_BILINEAR, 16><<<grid, NTHREADS, 0, st>>>(v, a, g, pad_mode, pad_value, pad_device, (T*)out);
     } else if (mode == AFB_NEAREST) {
         slice_fwd_kernel<T, AFB_NEAREST><<<grid, NTHREADS, 0, st>>>(v, a, g, pad_mode, pad_value, pad_device, (T*)out);
     } else {
         slice_fwd_kernel<T, AFB_BILINEAR><<<grid, NTHREADS, 0, st>>>(v, a, g, pad_mode, pad_value, pad_device, (T*)out);
     }
+    return (int)cudaGetLastError();
+}
+
+template <typename T>
+static int launch_bwd(const afb_volume* vol, const VolArgs& v, const ViewArgs& a, const OutGeom& g, int pad_mode, float pad_value,
+                      const float* pad_device, const float* grad_out, float* d_vol, float* d_pad, double* acc, cudaStream_t st) {
+    const dim3 grid = slice_grid(g, v.B * a.V);
+    const int vb = channels_last_vec(vol, (int)sizeof(T), d_vol, 32);
+    // measured on the B200 (384 slices, C = 8 fp32): LDG.256 x 4 corners in flight 0.689 ms, LDG.128 x 4: 0.718,
+    // LDG.128 x 8 (the earlier kernel): 0.702
+    constexpr int WIDE = sizeof(T) >= 4 ? 32 : 16;
+#define AFB_CLB(VB) slice_bwd_cl_kernel<T, VB, 4><<<grid, NTHREADS, 0, st>>>(v, a, g, pad_mode, pad_value, pad_device, grad_out, d_vol, d_pad, acc)
+    if (vb == 32) AFB_CLB(WIDE);
+    else if (vb == 16) AFB_CLB(16);
+#undef AFB_CLB
+    else
+        slice_bwd_kernel<T><<<grid, NTHREADS, 0, st>>>(v, a, g, pad_mode, pad_value, pad_device, grad_out, d_vol, d_pad, acc);
     return (int)cudaGetLastError();
 }
 
@@ -342,23 +414,15 @@ extern "C" int afb_slice_bwd(const afb_volume* vol, const afb_views* views, int 
     if (a.kind == AFB_AFFINE_PARAMS && d_affine && !views->params) return AFB_EINVAL;
     const int S = v.B * a.V;
     const OutGeom g = make_geom(Do, Ho, Wo);
-    const dim3 grid = slice_grid(g, S);
     double* acc = (double*)workspace;
     cudaStream_t st = (cudaStream_t)stream;
     if (grad_out) {     // grad_out == NULL: chain-only (nearest / integer volumes): only the upstream grad is propagated
-#define AFB_BWD(T)                                                                                                              \
-    if (channels_last_ok(vol, Vec16<T>::N, d_vol))                                                                              \
-        slice_bwd_cl_kernel<T><<<grid, NTHREADS, 0, st>>>(v, a, g, pad_mode, pad_value, pad_device, grad_out, d_vol, d_pad, acc); \
-    else                                                                                                                        \
-        slice_bwd_kernel<T><<<grid, NTHREADS, 0, st>>>(v, a, g, pad_mode, pad_value, pad_device, grad_out, d_vol, d_pad, acc)
         switch (vol->dtype) {
-            case AFB_F32: AFB_BWD(float); break;
-            case AFB_BF16: AFB_BWD(__nv_bfloat16); break;
-            case AFB_F16: AFB_BWD(__half); break;
+            case AFB_F32: rc = launch_bwd<float>(vol, v, a, g, pad_mode, pad_value, pad_device, grad_out, d_vol, d_pad, acc, st); break;
+            case AFB_BF16: rc = launch_bwd<__nv_bfloat16>(vol, v, a, g, pad_mode, pad_value, pad_device, grad_out, d_vol, d_pad, acc, st); break;
+            case AFB_F16: rc = launch_bwd<__half>(vol, v, a, g, pad_mode, pad_value, pad_device, grad_out, d_vol, d_pad, acc, st); break;
             default: return AFB_EDTYPE;
         }
-#undef AFB_BWD
-        rc = (int)cudaGetLastError();
         if (rc != 0) return rc;
     }
     if (!d_affine && !d_gpre) {
@@ -375,6 +439,8 @@ extern "C" int afb_slice_pad_grad(const afb_volume* vol, const afb_views* views,
     if (rc != AFB_OK) return rc;
     if (!grad_out || !d_pad) return AFB_EINVAL;
     const OutGeom g = make_geom(Do, Ho, Wo);
-    slice_pad_grad_kernel<<<slice_grid(g, v.B * a.V), NTHREADS, 0, (cudaStream_t)stream>>>(v, a, g, grad_out, d_pad);
+    const dim3 tiles = slice_grid(g, v.B * a.V);
+    const dim3 grid((tiles.x + PAD_TILES - 1) / PAD_TILES, tiles.y);
+    slice_pad_grad_kernel<<<grid, NTHREADS, 0, (cudaStream_t)stream>>>(v, a, g, (int)tiles.x, grad_out, d_pad);
     return (int)cudaGetLastError();
 }

@@ -73,6 +73,48 @@ def volume_min(volume: torch.Tensor, with_mask: bool = False) -> torch.Tensor:
     return out
 
 
+def min_record_alloc(n_elements: int, device) -> torch.Tensor:
+    """Uninitialised chunk record (``afb_min_mask_bytes``) for an fp32 tensor of ``n_elements``."""
+    return torch.empty(int(L.lib().afb_min_mask_bytes(int(n_elements))), dtype=torch.uint8, device=device)
+
+
+def onehot_expand(label_map: torch.Tensor, num_classes: int, out_label: Optional[torch.Tensor] = None,
+                  out_soft: Optional[torch.Tensor] = None, record: Optional[torch.Tensor] = None,
+                  total_elements: Optional[int] = None, elem_offset: int = 0) -> None:
+    """``one_hot(label_map, C)`` (int64, into ``out_label``) and its ``.float()`` (into ``out_soft``) in one launch
+    (``running/run_dl.py:261-264``); both outputs are contiguous ``[..., C]`` buffers (view them with
+    ``.permute(0,4,1,2,3)`` to get the reference's ``[B,C,D,H,W]`` tensors).  With ``record`` the chunk record of the
+    soft volume is written at ``elem_offset`` of a tensor of ``total_elements`` fp32 values (see
+    :func:`min_count_from_record`), which replaces the separate ``volume.min()`` pass."""
+    L.require_cuda(label_map, "label_map")
+    assert not label_map.dtype.is_floating_point and label_map.is_contiguous()
+    n_vox = label_map.numel()
+    for t, dt in ((out_label, torch.int64), (out_soft, torch.float32)):
+        if t is not None:
+            assert t.is_cuda and t.dtype == dt and t.is_contiguous() and t.numel() == n_vox * num_classes
+    tot = int(total_elements) if total_elements is not None else n_vox * num_classes
+    dev = label_map.device
+    with torch.cuda.device(dev):
+        L.check(L.lib().afb_onehot_expand(L.ptr(label_map), L.DTYPES[label_map.dtype], n_vox, int(num_classes), L.ptr(out_label),
+                                          L.ptr(out_soft), L.ptr(record), tot, int(elem_offset), L.stream_ptr(dev)),
+                "afb_onehot_expand")
+
+
+def min_count_from_record(record: torch.Tensor, n_elements: int) -> torch.Tensor:
+    """``[min, multiplicity]`` of an fp32 tensor from its chunk record alone; the record rides along as ``._afb_mask`` so
+    that the result can be passed as ``soft_pad`` / ``pad`` and serve MinBackward (same contract as
+    ``volume_min(..., with_mask=True)``)."""
+    lib = L.lib()
+    dev = record.device
+    with torch.cuda.device(dev):
+        ws = torch.empty(int(lib.afb_volume_min_workspace_bytes()), dtype=torch.uint8, device=dev)
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        L.check(lib.afb_min_count_from_mask(L.ptr(record), int(n_elements), L.ptr(out), L.ptr(ws), L.stream_ptr(dev)),
+                "afb_min_count_from_mask")
+    out._afb_mask = record
+    return out
+
+
 @dataclass
 class ViewSpec:
     """Python mirror of ``afb_views`` (include/afb200.h)."""

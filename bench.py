@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--volumes", type=int, default=64, help="volumes per GPU (weak scaling)")
     ap.add_argument("--views", type=int, default=6)
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-group", type=int, default=8, help="volumes per PCIe upload group of the e2e leg")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
@@ -326,12 +327,22 @@ def run_ours(args):
     h2d = host_lab.numel() * host_lab.element_size() + host_img.numel() * host_img.element_size()
     d2h = g_host.numel() * 4 + ga_host.numel() * 4
 
+    from acquisition_focus_b200.running.host_input import upload_one_hot
+
+    def step_with_pads(soft_t, label_t, image_t, pad_s, pad_i):
+        params.grad = None
+        ys, yl, yi, ga, nii_o, theta = AF.acquire_views(soft_t, label_t, image_t, nii, gpre, params, init, offset_clip=OFFSET_CLIP,
+                                                        zoom_clip=ZOOM_CLIP, spat=S, slice_fov_mm=fov_mm, slice_fov_vox=fov_vox,
+                                                        soft_pad=pad_s, image_pad=pad_i)
+        torch.autograd.backward([ys], [go])
+        return par.reduce_view_grads(params.grad), ga, soft_t.grad
+
     def e2e_step():
-        lab_dev = host_lab.to(dev, non_blocking=True)
-        img_dev = host_img.to(dev, non_blocking=True)
-        label_t, soft_t = one_hot_volumes(lab_dev)
-        soft_t.requires_grad_(True)
-        g, ga = step(soft_t, label_t, img_dev)
+        # public host-side entry: groups of volumes cross PCIe on a copy stream while the groups that have arrived are
+        # expanded to the int64 + fp32 one-hot volumes (run_dl.py:261-264) together with the soft volume's min record
+        db = upload_one_hot(host_lab, host_img, NUM_CLASSES, dev, group_volumes=args.e2e_group)
+        soft_t = db.soft_label.requires_grad_(True)
+        g, ga, dvol = step_with_pads(soft_t, db.label, db.image, db.soft_pad, db.image_pad)
         g_host.copy_(g, non_blocking=True)
         ga_host.copy_(ga.detach(), non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
@@ -389,7 +400,9 @@ def run_ours(args):
             "data": "synthetic", "config": workload_config(args), "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": args.e2e_steps,
-                    "what": "pinned host index-label int64 + image fp32 -> H2D -> device one-hot -> same step -> D2H reduced dTheta + grid affines"},
+                    "what": "pinned host index-label int64 + image fp32 -> running.host_input.upload_one_hot (H2D in groups of "
+                            f"{args.e2e_group} volumes on a copy stream, fused one-hot expansion + min record of the arrived groups on the "
+                            "compute stream) -> same acquisition fwd+bwd (dVolume + dTheta) -> D2H reduced dTheta + grid affines"},
             "gpu_launches": LAUNCHES_PER_STEP * args.steps, "roofline": roofline, "cpu_baseline": cpu_base,
             "kernels": breakdown, "l2_gbs_measured": l2_gbs, "variants": variants}
     print(json.dumps(line))

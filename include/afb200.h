@@ -124,6 +124,21 @@ int afb_volume_min_mask(const float* data, int64_t n_elements, float* out_min_co
 int afb_min_grad_fill_mask(const void* mask, int64_t n_elements, const float* min_count, const float* d_pad,
                            float* d_vol, void* stream);
 
+/* ---- one-hot materialisation (running/run_dl.py:261-264) fused with the min record ---------- */
+/* labels: n_voxels integers (label_dtype: AFB_U8/I16/I32/I64).  Writes, channels-last ([voxel][class], i.e. the strides
+ * of `one_hot(label, C).permute(0,4,1,2,3)` and of its `.float()`):
+ *   onehot_i64 (nullable) : int64 one-hot, what run_dl.py:261-262 hands the nearest-neighbour label slicing
+ *   soft_f32   (nullable) : fp32 one-hot, what run_dl.py:263-264 hands the bilinear soft-label slicing
+ * and, when `mask` is given, the soft volume's chunk record at its place inside the record of a tensor of
+ * total_elements fp32 values that this range starts at element elem_offset of (a multiple of 512; ranges other than
+ * the last must also hold a multiple of 512 elements): a host batch can be expanded range by range while later
+ * ranges are still crossing PCIe.  afb_min_count_from_mask then gives [min, multiplicity] of the whole tensor from
+ * the record alone - no 4 B/voxel min pass over a volume this library produced itself.
+ * Labels outside [0, num_classes) give an all-zero voxel (torch's one_hot raises instead).                       */
+int afb_onehot_expand(const void* labels, int label_dtype, int64_t n_voxels, int num_classes, int64_t* onehot_i64,
+                      float* soft_f32, void* mask, int64_t total_elements, int64_t elem_offset, void* stream);
+int afb_min_count_from_mask(const void* mask, int64_t n_elements, float* out_min_count, void* workspace, void* stream);
+
 /* ---- view prologue: raw view input -> grid affine, once per acquisition -------------------------
  * Computes for all S = B*V slices what nifti_utils.py:36-71 and learnable_transform.py:144-230,262-289
  * compute on the host in ~100 tiny fp32/fp64 torch ops: state (for the samplers), grid_affine_out
