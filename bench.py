@@ -378,7 +378,7 @@ def run_ours(args):
     breakdown, roofline, l2_gbs = ({}, None, None)
     if single and not args.no_breakdown:
         breakdown, l2_gbs = kernel_breakdown(AF, dev, soft, label, image, nii, gpre, params, init, go, fov_mm, fov_vox, nv, V)
-        roofline = make_roofline(breakdown, l2_gbs)
+        roofline = make_roofline(breakdown, l2_gbs, nv)
 
     variants = {}
     if single and not args.no_breakdown:
@@ -482,9 +482,9 @@ def kernel_breakdown(AF, dev, soft, label, image, nii, gpre, params, init, go, f
     spec = AF.prepare_views(spec, nv, (S, S, S), fov_vox, dev)[0]
     sd = soft.detach()
     t = _time(lambda: AF._slice_forward_raw(sd, spec, fov_vox, L.BILINEAR, L.PAD_DEVICE, 0.0, pad_s), dev)
-    out["slice_fwd(soft C=8 bilinear)"] = {"kernel": "slice_fwd_cl_kernel<float, 0>", "ms": t, "bytes": nS * Npix * NUM_CLASSES * 36, "bound": "l2"}
+    out["slice_fwd(soft C=8 bilinear)"] = {"kernel": "slice_fwd_cl_kernel<float, 0", "ms": t, "bytes": nS * Npix * NUM_CLASSES * 36, "bound": "l2"}
     t = _time(lambda: AF._slice_forward_raw(label, spec, fov_vox, L.NEAREST, L.PAD_ZERO, 0.0, None), dev)
-    out["slice_fwd(label C=8 int64 nearest)"] = {"kernel": "slice_fwd_cl_kernel<long, 1>", "ms": t, "bytes": nS * Npix * NUM_CLASSES * 16, "bound": "l2"}
+    out["slice_fwd(label C=8 int64 nearest)"] = {"kernel": "slice_fwd_cl_kernel<long, 1", "ms": t, "bytes": nS * Npix * NUM_CLASSES * 16, "bound": "l2"}
     t = _time(lambda: AF._slice_forward_raw(image, spec, fov_vox, L.BILINEAR, L.PAD_DEVICE, 0.0, pad_i), dev)
     out["slice_fwd(image C=1 bilinear)"] = {"kernel": "slice_fwd_kernel<float, 0>", "ms": t, "bytes": nS * Npix * 36, "bound": "l2"}
     # backward pieces
@@ -495,7 +495,7 @@ def kernel_breakdown(AF, dev, soft, label, image, nii, gpre, params, init, go, f
     t = _time(lambda: L.check(lib.afb_slice_pad_grad(C.byref(vd), C.byref(vs), S, S, 1, L.ptr(go), L.ptr(d_pad), st), "afb_slice_pad_grad"), dev)
     out["slice_pad_grad"] = {"kernel": "slice_pad_grad_kernel", "ms": t, "bytes": nS * Npix * NUM_CLASSES * 4, "bound": "hbm"}
     t = _time(lambda: L.check(lib.afb_min_grad_fill_mask(L.ptr(pad_s._afb_mask), sd.numel(), L.ptr(pad_s), L.ptr(d_pad), L.ptr(d_vol), st), "afb_min_grad_fill_mask"), dev)
-    out["min_grad_fill_mask(dVolume)"] = {"kernel": "min_grad_fill_mask_kernel", "ms": t, "bytes": sd.numel() * 4 + sd.numel() // 8, "bound": "hbm"}
+    out["min_grad_fill_mask(dVolume)"] = {"kernel": "min_grad_fill_mask_kernel<", "ms": t, "bytes": sd.numel() * 4 + sd.numel() // 8, "bound": "hbm"}
     t = _time(lambda: L.check(lib.afb_min_grad_fill(L.ptr(sd), L.F32, sd.numel(), L.ptr(pad_s), L.ptr(d_pad), L.ptr(d_vol), st), "afb_min_grad_fill"), dev)
     out["min_grad_fill(dVolume, re-reads the volume) [not in step]"] = {"kernel": "min_grad_fill_kernel<float>", "ms": t, "bytes": sd.numel() * 8, "bound": "hbm"}
 
@@ -503,24 +503,29 @@ def kernel_breakdown(AF, dev, soft, label, image, nii, gpre, params, init, go, f
         L.check(lib.afb_slice_bwd(C.byref(vd), C.byref(vs), S, S, 1, L.PAD_DEVICE, 0.0, L.ptr(pad_s), L.ptr(go), None,
                                   L.ptr(d_vol) if with_dvol else None, L.ptr(d_aff), None, None, L.ptr(ws), st), "afb_slice_bwd")
     t = _time(lambda: bwd(True), dev)
-    out["slice_bwd(soft, dVolume+dTheta)"] = {"kernel": "slice_bwd_cl_kernel<float>", "ms": t, "bytes": nS * Npix * NUM_CLASSES * (32 + 4 + 32), "bound": "l2"}
+    out["slice_bwd(soft, dVolume+dTheta)"] = {"kernel": "slice_bwd_cl_kernel<float", "ms": t, "bytes": nS * Npix * NUM_CLASSES * (32 + 4 + 32), "bound": "l2"}
     t = _time(lambda: bwd(False), dev)
-    out["slice_bwd(soft, dTheta only) [not in step]"] = {"kernel": "slice_bwd_cl_kernel<float>", "ms": t, "bytes": nS * Npix * NUM_CLASSES * (32 + 4), "bound": "l2"}
+    out["slice_bwd(soft, dTheta only) [not in step]"] = {"kernel": "slice_bwd_cl_kernel<float", "ms": t, "bytes": nS * Npix * NUM_CLASSES * (32 + 4), "bound": "l2"}
     for k, v in out.items():
         v["gbs"] = v["bytes"] / (v["ms"] * 1e-3) / 1e9
     return out, l2_gbs
 
 
-def ncu_traffic(kernel_key):
+def ncu_traffic(kernel_prefix, nv):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel, from the committed `ncu --set full` capture of
-    this same workload (profiles/ncu_traffic.json, written by profiles/ncu_summary.py --traffic); None if not captured."""
+    this workload at a smaller volume count (profiles/ncu_traffic.json, written by profiles/ncu_summary.py --traffic),
+    scaled linearly to `nv` volumes; None if not captured."""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if not os.path.exists(path):
+    if not os.path.exists(path) or not kernel_prefix:
         return None
-    return json.load(open(path)).get("kernels", {}).get(kernel_key)
+    d = json.load(open(path))
+    for name, val in d.get("kernels", {}).items():
+        if name.startswith(kernel_prefix):
+            return val * nv / d.get("volumes", nv)
+    return None
 
 
-def make_roofline(breakdown, l2_gbs):
+def make_roofline(breakdown, l2_gbs, nv):
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         hbm, src = float(json.load(open(peaks_path))["hbm_gbs"]), "of measured (MEASURED_PEAKS.json hbm_gbs)"
@@ -533,7 +538,7 @@ def make_roofline(breakdown, l2_gbs):
     for v in breakdown.values():
         v["frac"] = None if v["bound"] == "latency" else v["gbs"] / (hbm if v["bound"] == "hbm" else l2_gbs)
     return {"kernel": name, "bound": k["bound"], "achieved": k["gbs"], "peak": peak, "unit": "GB/s", "frac": k["gbs"] / peak,
-            "traffic": ncu_traffic(k.get("kernel", "")), "cuda_kernel": k.get("kernel"), "peak_source": src if k["bound"] == "hbm" else "L2 read bandwidth measured in this run: afb_probe_read, 64 passes over a 32 MiB L2-resident buffer in one launch",
+            "traffic": ncu_traffic(k.get("kernel", ""), nv), "cuda_kernel": k.get("kernel"), "peak_source": src if k["bound"] == "hbm" else "L2 read bandwidth measured in this run: afb_probe_read, 64 passes over a 32 MiB L2-resident buffer in one launch",
             "algorithmic_bytes_per_launch": k["bytes"], "ms_per_launch": k["ms"]}
 
 
