@@ -26,6 +26,7 @@ struct AxisConst {  // per output axis constants, computed on the host in fp32 (
     float step;     // 2/(K-1)   (0 for K==1)
     float km1;      // K-1
     float kf;       // K
+    float inv_k;    // 1/K when K is a power of two (then x / K == x * inv_k bit for bit), else 0
     int K;
 };
 
@@ -35,6 +36,7 @@ __host__ inline AxisConst make_axis(int K) {
     a.km1 = (float)(K - 1);
     a.kf = (float)K;
     a.step = K > 1 ? 2.0f / (float)(K - 1) : 0.0f;
+    a.inv_k = (K & (K - 1)) == 0 ? 1.0f / (float)K : 0.0f;
     return a;
 }
 
@@ -48,7 +50,10 @@ __device__ __forceinline__ float base_coord(int idx, const AxisConst& a) {
     } else {
         lin = __fmaf_rn(-a.step, (float)(a.K - 1 - idx), 1.0f);
     }
-    return __fdiv_rn(__fmul_rn(lin, a.km1), a.kf);
+    // division by a power of two is an exact exponent shift (|lin * (K-1)| is 0 or >= 2/K, far from the subnormals),
+    // so the multiply gives the same bits as ATen's division without the ~20-instruction IEEE divide
+    const float num = __fmul_rn(lin, a.km1);
+    return a.inv_k != 0.0f ? __fmul_rn(num, a.inv_k) : __fdiv_rn(num, a.kf);
 }
 
 __device__ __forceinline__ float grid_coord(const float* t /*row of 4*/, float x, float y, float z) {
@@ -131,7 +136,7 @@ struct ViewArgs {
 };
 
 // Everything the forward prologue produces; lives in shared memory.  The backward chain reads it.
-struct ViewState {
+struct alignas(16) ViewState {
     float g[16];           // G' (fp32, what the sampler uses and nifti_grid_sample returns)
     double P[16];          // pre_grid_sample_affine as fp64
     double n[3];           // column norms of P[:3,:3]

@@ -33,9 +33,10 @@ __device__ __forceinline__ void mm_merge(float& m, float& n, float m2, float n2)
 // chunk*512 + j*128 + l*4 + e)
 // CTA reduction of each lane's (min, multiplicity), then the last CTA to arrive reduces the per-CTA partials into out[0..1]
 // and re-arms the counter.  Called by all threads of the CTA.
+template <int NT = MM_THREADS>
 __device__ __forceinline__ void mm_finish(float gm, float gc, MinCountF* __restrict__ partial, unsigned* __restrict__ counter,
                                           float* __restrict__ out) {
-    __shared__ float sm[MM_THREADS / 32], sn[MM_THREADS / 32];
+    __shared__ float sm[NT / 32], sn[NT / 32];
     __shared__ bool last;
     const int t = threadIdx.x, w = t >> 5, lane = t & 31;
 #pragma unroll
@@ -46,7 +47,7 @@ __device__ __forceinline__ void mm_finish(float gm, float gc, MinCountF* __restr
     if (lane == 0) { sm[w] = gm; sn[w] = gc; }
     __syncthreads();
     if (t == 0) {
-        for (int k = 1; k < MM_THREADS / 32; ++k) mm_merge(gm, gc, sm[k], sn[k]);
+        for (int k = 1; k < NT / 32; ++k) mm_merge(gm, gc, sm[k], sn[k]);
         partial[blockIdx.x].m = gm;
         partial[blockIdx.x].n = gc;
         __threadfence();
@@ -56,7 +57,7 @@ __device__ __forceinline__ void mm_finish(float gm, float gc, MinCountF* __restr
     if (!last) return;
     __threadfence();
     gm = INFINITY; gc = 0.0f;
-    for (int i = t; i < (int)gridDim.x; i += MM_THREADS) {
+    for (int i = t; i < (int)gridDim.x; i += NT) {
         const float2 pc = __ldcg(reinterpret_cast<const float2*>(partial) + i);
         mm_merge(gm, gc, pc.x, pc.y);
     }
@@ -69,7 +70,7 @@ __device__ __forceinline__ void mm_finish(float gm, float gc, MinCountF* __restr
     if (lane == 0) { sm[w] = gm; sn[w] = gc; }
     __syncthreads();
     if (t == 0) {
-        for (int k = 1; k < MM_THREADS / 32; ++k) mm_merge(gm, gc, sm[k], sn[k]);
+        for (int k = 1; k < NT / 32; ++k) mm_merge(gm, gc, sm[k], sn[k]);
         out[0] = gm;
         out[1] = gc;
         *counter = 0u;
@@ -92,6 +93,26 @@ __device__ __forceinline__ void mm_load_chunk(const float* __restrict__ data, lo
     }
 }
 
+// chunk minimum + "== minimum" bits of the 16 values this lane holds; writes the record, merges into the lane's running pair
+__device__ __forceinline__ void mm_chunk_record(const float4* v, long long ch, int lane, float* __restrict__ chunk_min,
+                                                unsigned short* __restrict__ bits, float& gm, float& gc) {
+    float c = INFINITY;
+#pragma unroll
+    for (int j = 0; j < MM_LOADS; ++j) c = fminf(fminf(fminf(c, v[j].x), fminf(v[j].y, v[j].z)), v[j].w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c = fminf(c, __shfl_xor_sync(0xffffffffu, c, o));
+    unsigned b = 0u;
+#pragma unroll
+    for (int j = 0; j < MM_LOADS; ++j) {
+        const unsigned q = (v[j].x == c ? 1u : 0u) | (v[j].y == c ? 2u : 0u) | (v[j].z == c ? 4u : 0u) | (v[j].w == c ? 8u : 0u);
+        b |= q << (4 * j);
+    }
+    bits[ch * 32 + lane] = (unsigned short)b;
+    if (lane == 0) chunk_min[ch] = c;
+    // chunk minimum with this lane's share of its multiplicity (lanes that do not attain c contribute 0)
+    mm_merge(gm, gc, c, (float)__popc(b));
+}
+
 // A register double buffer (next chunk requested before the current one is reduced) was measured SLOWER on the
 // B200 (0.740 vs 0.719 ms per 4.3 GB: 63 registers cost two resident CTAs per SM), as was sizing the grid to exactly
 // one resident wave (0.731): the plain loop below at 148 x 8 CTAs reads at 6.1-6.2 TB/s.
@@ -105,21 +126,7 @@ volume_min_mask_kernel(const float* __restrict__ data, long long n, long long n_
     for (long long ch = (long long)blockIdx.x * (MM_THREADS / 32) + w; ch < n_chunks; ch += warps) {
         float4 v[MM_LOADS];
         mm_load_chunk(data, n, ch, lane, v);
-        float c = INFINITY;
-#pragma unroll
-        for (int j = 0; j < MM_LOADS; ++j) c = fminf(fminf(fminf(c, v[j].x), fminf(v[j].y, v[j].z)), v[j].w);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c = fminf(c, __shfl_xor_sync(0xffffffffu, c, o));
-        unsigned b = 0u;
-#pragma unroll
-        for (int j = 0; j < MM_LOADS; ++j) {
-            const unsigned q = (v[j].x == c ? 1u : 0u) | (v[j].y == c ? 2u : 0u) | (v[j].z == c ? 4u : 0u) | (v[j].w == c ? 8u : 0u);
-            b |= q << (4 * j);
-        }
-        bits[ch * 32 + lane] = (unsigned short)b;
-        if (lane == 0) chunk_min[ch] = c;
-        // chunk minimum with this lane's share of its multiplicity (lanes that do not attain c contribute 0)
-        mm_merge(gm, gc, c, (float)__popc(b));
+        mm_chunk_record(v, ch, lane, chunk_min, bits, gm, gc);
     }
     mm_finish(gm, gc, partial, counter, out);
 }

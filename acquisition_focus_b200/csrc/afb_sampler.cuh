@@ -19,6 +19,7 @@ struct OutGeom {
     int Do, Ho, Wo;
     int rows, cols;             // 2-D view of the output index space: slices (Wo==1): Do x Ho, else (Do*Ho) x Wo
     int tiles_c;
+    int tiles_c_shift;          // log2(tiles_c) when it is a power of two, else -1
 };
 
 struct Pix {
@@ -31,7 +32,9 @@ __device__ __forceinline__ Pix pixel_of_tile(const OutGeom& g, int tile) {
     const int w = tid >> 5, lane = tid & 31;
     const int lc = ((w & 1) << 3) + (lane & 7);
     const int lr = ((w >> 1) << 2) + (lane >> 3);
-    const int tr = tile / g.tiles_c, tc = tile % g.tiles_c;
+    int tr, tc;
+    if (g.tiles_c_shift >= 0) { tr = tile >> g.tiles_c_shift; tc = tile & (g.tiles_c - 1); }
+    else { tr = tile / g.tiles_c; tc = tile - tr * g.tiles_c; }
     const int row = tr * TILE + lr, col = tc * TILE + lc;
     Pix p;
     p.valid = row < g.rows && col < g.cols;
@@ -52,10 +55,14 @@ struct Sample {                 // un-normalised source coordinates of one outpu
 
 // grid affine of slice s: the first 12 floats of its ViewState (uniform address -> one broadcast per warp)
 __device__ __forceinline__ Sample sample_coords(const OutGeom& g, const Pix& p, const ViewArgs& va, int s, const VolArgs& vol) {
-    const float* __restrict__ G = reinterpret_cast<const float*>(reinterpret_cast<const ViewState*>(va.state) + s);
+    // three 16-byte broadcast loads (ViewState is 16-byte aligned and starts with G')
+    const float4* __restrict__ G = reinterpret_cast<const float4*>(reinterpret_cast<const ViewState*>(va.state) + s);
     float t[12];
 #pragma unroll
-    for (int q = 0; q < 12; ++q) t[q] = __ldg(G + q);
+    for (int q = 0; q < 3; ++q) {
+        const float4 r = __ldg(G + q);
+        t[4 * q] = r.x; t[4 * q + 1] = r.y; t[4 * q + 2] = r.z; t[4 * q + 3] = r.w;
+    }
     Sample sm;
     sm.bx = base_coord(p.k, g.ax);
     sm.by = base_coord(p.j, g.ay);
@@ -213,6 +220,9 @@ inline OutGeom make_geom(int Do, int Ho, int Wo) {
     g.Do = Do; g.Ho = Ho; g.Wo = Wo;
     if (Wo == 1) { g.rows = Do; g.cols = Ho; } else { g.rows = Do * Ho; g.cols = Wo; }
     g.tiles_c = (g.cols + TILE - 1) / TILE;
+    g.tiles_c_shift = -1;
+    for (int sh = 0; sh < 31; ++sh)
+        if ((1 << sh) == g.tiles_c) g.tiles_c_shift = sh;
     return g;
 }
 

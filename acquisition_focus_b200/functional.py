@@ -18,6 +18,7 @@ plus :func:`r6_to_matrix` (``utils/transform_utils.py:27-58``) and :func:`embed_
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple
 
@@ -184,14 +185,15 @@ def prepare_views(spec: ViewSpec, B: int, in_size, out_size, device):
     return spec.replace(state=state), ga, nii, th
 
 
-def _slice_forward_raw(volume, spec: ViewSpec, out_size, mode, pad_mode, pad_value, pad_dev):
+def _slice_forward_raw(volume, spec: ViewSpec, out_size, mode, pad_mode, pad_value, pad_dev, out=None):
     """One sampler launch over all slices; ``spec.state`` must be attached (see prepare_views)."""
     lib = L.lib()
     B, Cc = volume.shape[:2]
     Do, Ho, Wo = (int(v) for v in out_size)
     dev = volume.device
     with torch.cuda.device(dev):
-        out = torch.empty((B, spec.V, Cc, Do, Ho, Wo), dtype=volume.dtype, device=dev)
+        if out is None:
+            out = torch.empty((B, spec.V, Cc, Do, Ho, Wo), dtype=volume.dtype, device=dev)
         vd, vs = L.volume_desc(volume), spec.struct()
         L.check(lib.afb_slice_fwd(C.byref(vd), C.byref(vs), Do, Ho, Wo, mode, pad_mode, float(pad_value), L.ptr(pad_dev),
                                   L.ptr(out), L.stream_ptr(dev)), "afb_slice_fwd")
@@ -332,8 +334,18 @@ def slice_with_pre_affine(volume, nii_affine, pre_affine, fov_mm, fov_vox, is_la
     return out[:, 0], ga[:, 0], nii[:, 0]
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev) -> "torch.cuda.Stream":
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(key)
+    return _SIDE_STREAMS[key]
+
+
 def acquire_views(x_soft_label, x_label, x_image, nifti_affine, gpre, params, init, *, offset_clip, zoom_clip,
-                  spat, slice_fov_mm, slice_fov_vox, soft_pad="global_min", image_pad="global_min"):
+                  spat, slice_fov_mm, slice_fov_vox, soft_pad="global_min", image_pad="global_min", overlap_streams=None):
     """Fused tail of ``AffineTransformModule.forward`` for all views at once.
 
     x_soft_label ``[B,C,D,H,W]`` float (grad flows), x_label ``[B,C,D,H,W]`` int (nearest, no grad) or None,
@@ -344,6 +356,8 @@ def acquire_views(x_soft_label, x_label, x_image, nifti_affine, gpre, params, in
     input the reference builds with ``torch.cat(slices, dim=1)`` (running/run_dl.py:325)."""
     L.require_cuda(x_soft_label, "x_soft_label")
     dev = x_soft_label.device
+    if overlap_streams is None:
+        overlap_streams = os.environ.get("AFB_OVERLAP", "1") != "0"
     B, V = gpre.shape[0], gpre.shape[1]
     NP = params.shape[-1]
     R = (NP - 7) // 3
@@ -354,13 +368,50 @@ def acquire_views(x_soft_label, x_label, x_image, nifti_affine, gpre, params, in
     p = params.to(dev, torch.float32).reshape(B * V, NP)
     spec = spec.replace(params=p.detach().contiguous())
     prepared = prepare_views(spec, B, x_soft_label.shape[2:], slice_fov_vox, dev)      # one prologue for everything below
-    y_soft, ga, nii, theta = _run_slice(x_soft_label, p, spec, slice_fov_vox, L.BILINEAR, soft_pad, prepared)
-    y_label = y_image = None
-    with torch.no_grad():
-        if x_label is not None and x_label.numel() > 0:
-            y_label = _run_slice(x_label, p.detach(), spec, slice_fov_vox, L.NEAREST, "zero", prepared)[0]
-        if x_image is not None and x_image.numel() > 0:
-            y_image = _run_slice(x_image, p.detach(), spec, slice_fov_vox, L.BILINEAR, image_pad, prepared)[0]
+
+    def no_grad_slicings():
+        yl = yi = None
+        with torch.no_grad():
+            if x_label is not None and x_label.numel() > 0:
+                yl = _run_slice(x_label, p.detach(), spec, slice_fov_vox, L.NEAREST, "zero", prepared)[0]
+            if x_image is not None and x_image.numel() > 0:
+                yi = _run_slice(x_image, p.detach(), spec, slice_fov_vox, L.BILINEAR, image_pad, prepared)[0]
+        return yl, yi
+
+    if overlap_streams and not isinstance(soft_pad, torch.Tensor):
+        # the label / image slicings (gather kernels, latency bound) run on a side stream UNDER the soft volume's min pass
+        # (HBM bound), then the soft slicing follows on the caller's stream.  Their outputs are allocated on the caller's
+        # stream and the side stream is joined before returning, so the caching allocator needs no cross-stream bookkeeping.
+        main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+        Do, Ho, Wo = (int(v) for v in slice_fov_vox)
+        has_l = x_label is not None and x_label.numel() > 0
+        has_i = x_image is not None and x_image.numel() > 0
+        xl = (x_label if _is_dense(x_label) else x_label.contiguous()) if has_l else None
+        xi = (x_image.detach() if _is_dense(x_image) else x_image.detach().contiguous()) if has_i else None
+        y_label = torch.empty((B, V, xl.shape[1], Do, Ho, Wo), dtype=xl.dtype, device=dev) if has_l else None
+        y_image = torch.empty((B, V, xi.shape[1], Do, Ho, Wo), dtype=xi.dtype, device=dev) if has_i else None
+        ws_i = torch.empty(int(L.lib().afb_volume_min_workspace_bytes()) + 16, dtype=torch.uint8, device=dev) if has_i else None
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            if has_l:
+                _slice_forward_raw(xl, prepared[0], slice_fov_vox, L.NEAREST, L.PAD_ZERO, 0.0, None, out=y_label)
+            if has_i:
+                pm, pv, pd = L.PAD_ZERO, 0.0, None
+                if isinstance(image_pad, torch.Tensor):
+                    pm, pd = L.PAD_DEVICE, image_pad
+                elif image_pad == "global_min":
+                    pd = ws_i[:8].view(torch.float32)
+                    L.check(L.lib().afb_volume_min(L.ptr(xi), L.DTYPES[xi.dtype], xi.numel(), L.ptr(pd), L.ptr(ws_i[16:]),
+                                                   L.stream_ptr(dev)), "afb_volume_min")
+                    pm = L.PAD_DEVICE
+                elif image_pad != "zero":
+                    pm, pv = L.PAD_VALUE, float(image_pad)
+                _slice_forward_raw(xi, prepared[0], slice_fov_vox, L.BILINEAR, pm, pv, pd, out=y_image)
+        y_soft, ga, nii, theta = _run_slice(x_soft_label, p, spec, slice_fov_vox, L.BILINEAR, soft_pad, prepared)
+        main.wait_stream(side)
+    else:
+        y_soft, ga, nii, theta = _run_slice(x_soft_label, p, spec, slice_fov_vox, L.BILINEAR, soft_pad, prepared)
+        y_label, y_image = no_grad_slicings()
     return y_soft, y_label, y_image, ga, nii, theta
 
 
