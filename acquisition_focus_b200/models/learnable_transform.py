@@ -21,6 +21,8 @@ import torch.nn as nn
 from .. import functional as AF
 from ..synthetic import random_aug_affine
 from ..utils.nifti_utils import nifti_grid_sample
+from ..utils.transform_utils import (angle_axis_to_rotation_matrix, compute_rotation_matrix_from_ortho6d,
+                                     normal_to_rotation_matrix)
 
 
 class DefaultLocalizationNet(nn.Module):
@@ -51,14 +53,17 @@ class AffineTransformModule(nn.Module):
         assert volume_fov_vox[0] == volume_fov_vox[1] == volume_fov_vox[2]
         assert optim_method in ["angle-axis", "normal-vector", "R6-vector"], \
             f"optim_method must be 'angle-axis', 'normal-vector' or 'R6-vector', not {optim_method}"
-        if optim_method != "R6-vector":
-            raise NotImplementedError("only the default 'R6-vector' parameterisation is on the CUDA path")
         if align_corners or rotate_slice_to_min_principle:
             raise NotImplementedError("align_corners / rotate_slice_to_min_principle are off in the reference "
                                       "defaults and not part of the accelerated path")
         self.optim_method = optim_method
-        self.ap_space = 6
-        self.init_theta_ap = nn.Parameter(torch.tensor([[1e-2, 0, 0, 0, 1e-2, 0]]), requires_grad=False)
+        if optim_method == "R6-vector":                       # fused into the CUDA view prologue
+            self.ap_space, self.optim_function = 6, compute_rotation_matrix_from_ortho6d
+            self.init_theta_ap = nn.Parameter(torch.tensor([[1e-2, 0, 0, 0, 1e-2, 0]]), requires_grad=False)
+        else:                                                 # 3-parameter closed forms -> the same CUDA sampler
+            self.ap_space = 3
+            self.optim_function = angle_axis_to_rotation_matrix if optim_method == "angle-axis" else normal_to_rotation_matrix
+            self.init_theta_ap = nn.Parameter(torch.zeros(3), requires_grad=False)
         self.volume_fov_mm = torch.as_tensor(volume_fov_mm)
         self.volume_fov_vox = torch.as_tensor(volume_fov_vox)
         self.slice_fov_vox = torch.as_tensor(slice_fov_vox)
@@ -100,21 +105,45 @@ class AffineTransformModule(nn.Module):
 
     def init_vector(self) -> torch.Tensor:
         """``[10]``: init_theta_ap | init_theta_t_offsets | init_theta_zp, the layout afb_views.init wants."""
+        assert self.optim_method == "R6-vector", "the fused view prologue takes R6 parameters"
         return torch.cat([self.init_theta_ap.reshape(6).float(), self.init_theta_t_offsets.reshape(3).float(),
                           self.init_theta_zp.reshape(1).float()])
 
     def get_init_affines(self):
         """Init rotation / translation / zoom 4x4s (reference :144-161); host-side convenience."""
         dev = self.init_theta_t_offsets.device
-        if dev.type == "cuda":
-            theta_a = AF.r6_to_matrix(self.init_theta_ap.view(1, 6))
-        else:
+        if dev.type != "cuda":
             raise RuntimeError("get_init_affines needs the module on a CUDA device (no CPU fallback)")
+        theta_a = self.optim_function(self.init_theta_ap.view(1, self.ap_space))
         theta_t = torch.eye(4, device=dev)[None].clone()
         theta_t[0, :3, 3] = self.init_theta_t_offsets
         z = self.init_theta_zp.view(1)
         theta_z = torch.diag_embed(torch.cat([z, z, z, torch.ones(1, device=dev)]))[None]
         return theta_a.float(), theta_t.float(), theta_z.float()
+
+    def get_gs_offsets_from_theta_tp(self, theta_tp):
+        """Soft-argmax offsets (reference :163-176, ``align_corners=False``): ``[B,3,R] -> [B,3]``."""
+        pos = (torch.softmax(theta_tp, dim=2) * self.arra.to(theta_tp).view(1, 1, self.vox_range)).sum(-1)
+        return (2.0 * pos + 1.0) / self.spat - 1.0
+
+    def theta_from_mlp_out(self, mlp_out):
+        """``T @ R @ Z`` from the MLP-head output with torch ops (reference :193-230, :262-272); the R6 method has this
+        fused into the CUDA prologue instead (``AF.acquire_views``), the other two parameterisations come through here."""
+        B, A, R = mlp_out.shape[0], self.ap_space, self.vox_range
+        dev = mlp_out.device
+        ap = mlp_out[:, :A] + self.init_theta_ap.view(1, A).to(dev)
+        zp = mlp_out[:, -1:] + self.init_theta_zp.view(1, 1).to(dev)
+        if self.optim_method == "normal-vector":
+            ap = ap / ap.norm(dim=1).view(-1, 1)
+        offs = self.get_gs_offsets_from_theta_tp(mlp_out[:, A:-1].view(B, 3, R))
+        if self.offset_clip_value == 0.0:
+            offs = 0.0 * offs
+        theta_t = torch.eye(4, device=dev)[None].repeat(B, 1, 1)
+        theta_t[:, :3, 3] = offs
+        z = self.zoom_clip_value * -(zp.tanh()) + 1.0
+        theta_z = torch.diag_embed(torch.cat([z, z, z, torch.ones(B, 1, device=dev)], dim=-1))
+        a0, t0, z0 = self.get_init_affines()
+        return (t0 @ theta_t) @ (a0 @ self.optim_function(ap)) @ (z0 @ theta_z)
 
     def mlp_head(self, x_soft_label, nifti_affine, grid_affine_pre_mlp):
         """LocalizationNet input (pre-oriented prescan volume, reference :248-255) -> ``[B, 6+3R+1]``."""
@@ -137,9 +166,11 @@ class AffineTransformModule(nn.Module):
         B = x_soft_label.shape[0]
         dev = x_soft_label.device
         gpre = grid_affine_pre_mlp.to(dev, torch.float32)
-        if theta_override is not None or not self.use_affine_theta:
+        if theta_override is not None or not self.use_affine_theta or self.optim_method != "R6-vector":
             if theta_override is not None:
                 theta = theta_override.detach().clone().to(dev, torch.float32)       # non-differentiable (:260)
+            elif self.use_affine_theta:
+                theta = self.theta_from_mlp_out(self.mlp_head(x_soft_label, nifti_affine, gpre))     # differentiable
             else:
                 a, t, z = self.get_init_affines()
                 theta = (t @ a @ z).repeat(B, 1, 1)
@@ -205,6 +236,7 @@ class ATModulesContainer(nn.ModuleList):
         ``mlp_outs``: optional list of ``[B, 6+3R+1]`` (else each module's LocalizationNet is run).
         Returns ``(y_soft[B,V,C,H,W,1], y_label, y_image, grid_affines[B,V,4,4], nii[B,V,4,4])``."""
         atms = list(self)
+        assert all(m.optim_method == "R6-vector" for m in atms), "the fused all-views acquisition takes R6 parameters"
         dev = x_soft_label.device
         gpre = torch.stack([g.to(dev, torch.float32) for g in view_pre_affines], dim=1)
         if mlp_outs is None:
@@ -226,6 +258,7 @@ class ATModulesContainer(nn.ModuleList):
         one-hot volume is materialised (``running/run_dl.py:261-264``); gradients flow to the view parameters only, which is
         all the reference's training step consumes.  ``modules``: the active view modules (default: all)."""
         atms = list(self) if modules is None else list(modules)
+        assert all(m.optim_method == "R6-vector" for m in atms), "the fused all-views acquisition takes R6 parameters"
         dev = label_map.device
         gpre = torch.stack([g.to(dev, torch.float32) for g in view_pre_affines], dim=1)
         if mlp_outs is None:

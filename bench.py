@@ -268,7 +268,20 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         import datetime
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))    # a hang dies in 2 min, not 10
+        # keep stdout to the single JSON line: NCCL prints its version banner to stdout when NCCL_DEBUG is set in the
+        # environment, so fd 1 points at stderr while the communicator is created (init + first collective)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))    # a hang dies in 2 min, not 10
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     nv, V = args.volumes, args.views
     h = make_host_inputs(nv, V, seed=1000 + rank)
     host_lab = h["lab"].pin_memory()

@@ -55,6 +55,52 @@ def r6_to_matrix(ortho: torch.Tensor) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------
+# f4  the two non-default rotation parameterisations    utils/transform_utils.py:62-178
+# ----------------------------------------------------------------------------
+def normal_to_matrix(normals: torch.Tensor) -> torch.Tensor:
+    """``normal_to_rotation_matrix`` (:62-103): the input columns are read as (nz, ny, nx); rows of R are the in-plane
+    direction (ny, -nx, 0)/d, its complement (nx nz, ny nz, -d^2)/d and the normal (nx, ny, nz), d = sqrt(nx^2+ny^2).
+    Degenerate (d = 0, e.g. the module's all-zero init) divides by zero exactly as the reference does."""
+    nz, ny, nx = normals[:, 0], normals[:, 1], normals[:, 2]
+    d = torch.sqrt(nx ** 2 + ny ** 2)
+    zero, one = torch.zeros_like(nx), torch.ones_like(nx)
+    rows = [ny / d, -nx / d, zero, zero,
+            nx * nz / d, ny * nz / d, -d, zero,
+            nx, ny, nz, zero,
+            zero, zero, zero, one]
+    return torch.stack(rows, dim=1).view(-1, 4, 4)
+
+
+def angle_axis_to_matrix(angle_axis: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    """``angle_axis_to_rotation_matrix`` (:106-178, after ceres/rotation.h): Rodrigues' formula with the reference's
+    double-eps normalisation ``w = r / (sqrt(|r|^2 + eps) + eps)`` where |r|^2 > eps, first-order ``I + [r]x`` otherwise;
+    both branches are evaluated and blended with 0/1 masks (so both contribute to autograd, as in the reference)."""
+    r = angle_axis
+    theta2 = (r.to(torch.float32)[:, None, :] @ r.to(torch.float32)[:, :, None]).squeeze(1)        # [N,1]  (:156-159)
+    theta = torch.sqrt(theta2 + eps)                                                                # :127
+    w = r / (theta + eps)                                                                           # :128
+    wx, wy, wz = w[:, 0:1], w[:, 1:2], w[:, 2:3]
+    c, s = torch.cos(theta), torch.sin(theta)
+    full = torch.cat([c + wx * wx * (1.0 - c), wx * wy * (1.0 - c) - wz * s, wy * s + wx * wz * (1.0 - c),
+                      wz * s + wx * wy * (1.0 - c), c + wy * wy * (1.0 - c), -wx * s + wy * wz * (1.0 - c),
+                      -wy * s + wx * wz * (1.0 - c), wx * s + wy * wz * (1.0 - c), c + wz * wz * (1.0 - c)], dim=1).view(-1, 3, 3)
+    rx, ry, rz = r[:, 0:1], r[:, 1:2], r[:, 2:3]
+    k1 = torch.ones_like(rx)
+    taylor = torch.cat([k1, -rz, ry, rz, k1, -rx, -ry, rx, k1], dim=1).view(-1, 3, 3)              # :146-151
+    big = (theta2 > eps).view(-1, 1, 1)
+    out = torch.eye(4).to(r.device).type_as(r).view(1, 4, 4).repeat(r.shape[0], 1, 1)
+    out[..., :3, :3] = big.type_as(theta2) * full + (~big).type_as(theta2) * taylor                 # :166-177
+    return out
+
+
+AP_SPACE = {"R6-vector": 6, "angle-axis": 3, "normal-vector": 3}
+
+
+def rotation_of(optim_method: str, ap: torch.Tensor) -> torch.Tensor:
+    return {"R6-vector": r6_to_matrix, "angle-axis": angle_axis_to_matrix, "normal-vector": normal_to_matrix}[optim_method](ap)
+
+
+# ----------------------------------------------------------------------------
 # a7  affine bookkeeping                               utils/nifti_utils.py:7-83,98-108,254-256
 # ----------------------------------------------------------------------------
 def column_norms(m: torch.Tensor) -> torch.Tensor:
@@ -187,22 +233,25 @@ def _zoom(z: torch.Tensor) -> torch.Tensor:
     return torch.diag_embed(torch.cat([z, z, z, ones], dim=-1))
 
 
-def view_theta(mlp_out, init_ap, init_t_offsets, init_zp, offset_clip_value, zoom_clip_value, spat):
+def view_theta(mlp_out, init_ap, init_t_offsets, init_zp, offset_clip_value, zoom_clip_value, spat, optim_method="R6-vector"):
     """learnable_transform.py:144-161 (init affines), :188-230 (batch affines),
-    :262-272 (composition).  ``mlp_out[B, 6+3R+1]`` is what LocalizationNet returns.
-    R6-vector parameterisation, ``use_affine_theta=True``, ``align_corners=False``."""
+    :262-272 (composition).  ``mlp_out[B, A+3R+1]`` is what LocalizationNet returns (A = 6 for the default R6-vector
+    parameterisation, 3 for angle-axis / normal-vector).  ``use_affine_theta=True``, ``align_corners=False``."""
     B = mlp_out.shape[0]
     R = offset_vox_range(offset_clip_value, spat)
-    assert mlp_out.shape[1] == 6 + 3 * R + 1
+    A = AP_SPACE[optim_method]
+    assert mlp_out.shape[1] == A + 3 * R + 1
     # init affines (:144-161)
-    a0 = r6_to_matrix(init_ap.view(1, 6)).to(torch.float32).repeat(B, 1, 1)
+    a0 = rotation_of(optim_method, init_ap.view(1, A)).to(torch.float32).repeat(B, 1, 1)
     t0 = _translation(init_t_offsets.view(1, 3).to(torch.float32)).repeat(B, 1, 1)
     z0 = _zoom(init_zp.view(1, 1).to(torch.float32)).repeat(B, 1, 1)
     # batch affines (:193-230); inits are added to the raw parameters as well (:198-199)
-    ap = mlp_out[:, :6] + init_ap.view(1, 6)
-    tp = mlp_out[:, 6:-1].view(B, 3, R)
+    ap = mlp_out[:, :A] + init_ap.view(1, A)
+    tp = mlp_out[:, A:-1].view(B, 3, R)
     zp = mlp_out[:, -1:] + init_zp.view(1, 1)
-    a_b = r6_to_matrix(ap)
+    if optim_method == "normal-vector":
+        ap = ap / ap.norm(dim=1).view(-1, 1)                                                # :204-205
+    a_b = rotation_of(optim_method, ap)
     pos = (F.softmax(tp, dim=2) * offset_positions(spat, R).to(tp).view(1, 1, R)).sum(-1)   # :165-168
     offs = (2.0 * pos + 1.0) / spat - 1.0                                                   # :174
     if offset_clip_value == 0.0:

@@ -117,15 +117,34 @@ def gold_slice_cfg1(R):
                         dvol_sum_w=_np(dv.sum(2)), dvol_absmax=np.float32(dv.abs().max().item()))
 
 
-def _run_atm(R, case):
+def gold_rotation_params(R):
+    """f4: the two non-default parameterisations, forward + gradient (utils/transform_utils.py:62-178)."""
+    from oracle import cases
+    tu = R.transform_utils
+    aa = cases.randn((9, 3), 61)
+    aa[0] = 0.0
+    aa[1] = 1e-4 * aa[1]                      # below the eps threshold: first-order branch
+    nv = cases.randn((9, 3), 62)
+    out = {}
+    for tag, fn, x in (("aa", tu.angle_axis_to_rotation_matrix, aa), ("nv", tu.normal_to_rotation_matrix, nv)):
+        xx = x.clone().requires_grad_(True)
+        m = fn(xx)
+        (m * cases.pattern(m.shape, 1.0)).sum().backward()
+        out.update({f"{tag}_in": _np(x), f"{tag}_mat": _np(m), f"{tag}_grad": _np(xx.grad)})
+    np.savez_compressed(os.path.join(GOLD, "rotation_params.npz"), **out)
+
+
+def _run_atm(R, case, optim_method="R6-vector", init_ap=None):
     B, V, S = case["B"], case["V"], case["S"]
     res = []
     for v in range(V):
         atm = R.AffineTransformModule(8, case["volume_fov_mm"], case["volume_fov_vox"], case["slice_fov_mm"],
-                                      case["slice_fov_vox"], optim_method="R6-vector",
+                                      case["slice_fov_vox"], optim_method=optim_method,
                                       offset_clip_value=case["offset_clip"], zoom_clip_value=case["zoom_clip"],
                                       view_id="p2CH")
         assert atm.vox_range == case["R"]
+        if init_ap is not None:
+            atm.set_init_theta_ap(init_ap)
         params = case["params"][v].clone().requires_grad_(True)
         atm.localization_net = _Stub(params)
         soft = case["soft"].clone().requires_grad_(True)
@@ -165,6 +184,24 @@ def gold_atm(R):
     np.savez_compressed(os.path.join(GOLD, "atm_s128.npz"), **out)
 
 
+def gold_atm_other_params(R):
+    """f4: AffineTransformModule.forward with optim_method angle-axis / normal-vector (32^3, 2 views).  The MLP-head outputs
+    are the R6 cases' with the first 3 of the 6 rotation parameters kept; normal-vector gets a non-degenerate init
+    (the reference's all-zero default divides by zero, learnable_transform.py:85-88 + transform_utils.py:83)."""
+    from oracle import cases
+    for method, init_ap in (("angle-axis", None), ("normal-vector", torch.tensor([0.2, -0.1, 1.0]))):
+        case = cases.atm_case(32, 2, 2, seed=71)
+        case["params"] = [torch.cat([0.4 * p[:, :3], p[:, 6:]], dim=1) for p in case["params"]]
+        res = _run_atm(R, case, optim_method=method, init_ap=init_ap)
+        out = {"gpre": np.stack([_np(g) for g in case["gpre"]]), "params": np.stack([_np(p) for p in case["params"]]),
+               "init_ap": _np(init_ap if init_ap is not None else torch.zeros(3))}
+        for v, r in enumerate(res):
+            out.update({f"ys{v}": _np(r["ys"]), f"yl{v}": _np(r["yl"]).astype(np.uint8), f"yi{v}": _np(r["yi"]),
+                        f"ga{v}": _np(r["ga"]), f"na{v}": _np(r["na"]), f"dparams{v}": _np(r["dparams"]),
+                        f"theta{v}": _np(r["theta"])})
+        np.savez_compressed(os.path.join(GOLD, "atm_s32_" + method.replace("-", "_") + ".npz"), **out)
+
+
 def gold_embed(R):
     from oracle import cases
     for tag, (S, c, V, B) in (("embed_s16", (16, 3, 2, 2)), ("embed_s8", (8, 4, 3, 2)), ("embed_s32", (32, 4, 6, 1))):
@@ -183,12 +220,10 @@ def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     R = load_reference()
-    write_view_affines(R)
-    gold_r6(R)
-    gold_slice_small(R)
-    gold_slice_cfg1(R)
-    gold_atm(R)
-    gold_embed(R)
+    groups = {"views": write_view_affines, "r6": gold_r6, "slice_small": gold_slice_small, "slice_cfg1": gold_slice_cfg1,
+              "atm": gold_atm, "embed": gold_embed, "rotation_params": gold_rotation_params, "atm_other": gold_atm_other_params}
+    for name in (sys.argv[1:] or list(groups)):          # python -m oracle.make_golden [group ...]
+        groups[name](R)
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 

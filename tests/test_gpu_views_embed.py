@@ -136,6 +136,37 @@ def test_module_forward_matches_oracle(afb):
     close(ga2, rga, 2e-6); close(ys2, rs, 2e-5)
 
 
+@pytest.mark.parametrize("method,init_ap", [("angle-axis", None), ("normal-vector", [0.2, -0.1, 1.0])])
+def test_module_other_parameterisations_golden(afb, golden_dir, method, init_ap):
+    """optim_method 'angle-axis' / 'normal-vector' through the drop-in module (closed-form rotation with
+    torch ops on the device -> CUDA sampler via the differentiable pre-affine) against the reference's own outputs."""
+    g = np.load(os.path.join(golden_dir, "atm_s32_" + method.replace("-", "_") + ".npz"))
+    case = cases.atm_case(32, 2, 2, seed=71)
+
+    class Stub(torch.nn.Module):
+        def __init__(self, p):
+            super().__init__(); self.p = torch.nn.Parameter(p)
+        def forward(self, x):
+            return self.p
+    for v in range(2):
+        atm = afb.AffineTransformModule(8, case["volume_fov_mm"], case["volume_fov_vox"], case["slice_fov_mm"], case["slice_fov_vox"],
+                                        optim_method=method, offset_clip_value=case["offset_clip"], zoom_clip_value=0.0, view_id="p2CH",
+                                        localization_net=Stub(torch.from_numpy(g["params"][v]).clone())).cuda()
+        assert atm.ap_space == 3 and atm.vox_range == case["R"]
+        if init_ap is not None:
+            atm.set_init_theta_ap(torch.tensor(init_ap).cuda())
+        ys, yl, yi, ga, nii = atm(case["soft"].cuda(), case["label"].cuda(), case["image"].cuda(), case["nii"].cuda(), case["gpre"][v].cuda())
+        close(atm.last_theta, g[f"theta{v}"], 2e-6, "theta")
+        close(ga, g[f"ga{v}"], 2e-6, "grid affine")
+        close(nii, g[f"na{v}"], 1e-6, "nii affine")
+        close(ys, g[f"ys{v}"], 2e-5, "soft slice")
+        close(yi, g[f"yi{v}"], 1e-4, "image slice")
+        mism = (yl.cpu().numpy().astype(np.uint8) != g[f"yl{v}"]).mean()
+        assert mism < 2e-3, mism                      # only pixels within an ulp of a rounding tie may flip (see DESIGN)
+        ((ys * cases.pattern(ys.shape, 1.0 + v).cuda()).sum() + (ga * cases.pattern(ga.shape, 2.0 + v).cuda()).sum()).backward()
+        close(atm.localization_net.p.grad, g[f"dparams{v}"], GRAD_REL, "dparams")
+
+
 @pytest.mark.parametrize("tag,shape", [("embed_s16", (16, 3, 2, 2)), ("embed_s8", (8, 4, 3, 2)), ("embed_s32", (32, 4, 6, 1))])
 def test_embed_golden(afb, golden_dir, tag, shape):
     S, c, V, B = shape

@@ -99,3 +99,40 @@ def test_embed(golden_dir, tag, shape):
     assert _close(np.stack([a.grad.numpy() for a in gas]), g["d_affines"], rel=1e-4)
     sp = O.skip_connector_sparse(x.detach(), [a.detach() for a in gas], V)
     assert _close(sp.numpy(), g["out"], rel=1e-5)
+
+
+# ---- the two non-default rotation parameterisations --------------------------------------------------
+@pytest.mark.parametrize("tag,fn", [("aa", "angle_axis"), ("nv", "normal")])
+def test_rotation_params(golden_dir, tag, fn):
+    """oracle restatement (bitwise forward) AND the product's host-side closed forms (device-agnostic torch ops, 1e-6)
+    against the reference's transform_utils.py:62-178."""
+    from acquisition_focus_b200.utils import transform_utils as T
+    g = np.load(os.path.join(golden_dir, "rotation_params.npz"))
+    oracle_fn = {"angle_axis": O.angle_axis_to_matrix, "normal": O.normal_to_matrix}[fn]
+    product_fn = {"angle_axis": T.angle_axis_to_rotation_matrix, "normal": T.normal_to_rotation_matrix}[fn]
+    for f, exact in ((oracle_fn, True), (product_fn, False)):
+        x = torch.from_numpy(g[f"{tag}_in"]).requires_grad_(True)
+        m = f(x)
+        if exact:
+            assert np.array_equal(m.detach().numpy(), g[f"{tag}_mat"])
+        else:
+            assert _close(m.detach().numpy(), g[f"{tag}_mat"], rel=1e-6)
+        (m * cases.pattern(m.shape, 1.0)).sum().backward()
+        assert _close(x.grad.numpy(), g[f"{tag}_grad"])
+
+
+@pytest.mark.parametrize("method,init_ap", [("angle-axis", None), ("normal-vector", [0.2, -0.1, 1.0])])
+def test_atm_other_parameterisations(golden_dir, method, init_ap):
+    g = np.load(os.path.join(golden_dir, "atm_s32_" + method.replace("-", "_") + ".npz"))
+    case = cases.atm_case(32, 2, 2, seed=71)
+    ia = torch.tensor(init_ap) if init_ap is not None else torch.zeros(3)
+    for v in range(2):
+        params = torch.from_numpy(g["params"][v]).requires_grad_(True)
+        theta = O.view_theta(params, ia, torch.zeros(3), torch.ones(1, 1), case["offset_clip"], 0.0, 32, optim_method=method)
+        assert np.array_equal(theta.detach().numpy(), g[f"theta{v}"])
+        ys, yl, yi, ga, na = O.atm_tail_forward(case["soft"], case["label"], case["image"], case["nii"], case["gpre"][v], theta,
+                                                case["slice_fov_mm"], case["slice_fov_vox"])
+        assert np.array_equal(ys.detach().numpy(), g[f"ys{v}"]) and np.array_equal(ga.detach().numpy(), g[f"ga{v}"])
+        assert np.array_equal(yl.numpy().astype(np.uint8), g[f"yl{v}"]) and np.array_equal(yi.numpy(), g[f"yi{v}"])
+        ((ys * cases.pattern(ys.shape, 1.0 + v)).sum() + (ga * cases.pattern(ga.shape, 2.0 + v)).sum()).backward()
+        assert _close(params.grad.numpy(), g[f"dparams{v}"])
