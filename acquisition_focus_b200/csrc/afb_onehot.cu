@@ -39,16 +39,16 @@ __device__ __forceinline__ void corner_labels(const L* __restrict__ src, const C
 template <typename L, int LABEL_OUT>      // LABEL_OUT: 0 none, 1 one-hot int64 [S,C,N], 2 index uint8 [S,N]
 __global__ void __launch_bounds__(NTHREADS, 3)
 onehot_fwd_kernel(LabArgs la, ViewArgs va, OutGeom g, float* __restrict__ y_soft, void* __restrict__ y_label) {
-    const int s = blockIdx.y;
+    const int s = blockIdx.z * va.V + blockIdx.y;      // grid = (tiles, V, B): no integer division for the batch index
     const Pix p = pixel_of_thread(g);
     if (!p.valid) return;
     VolArgs vol;
     vol.data = la.data; vol.B = la.B; vol.C = 1; vol.D = la.D; vol.H = la.H; vol.W = la.W;
     vol.sB = la.sB; vol.sC = 0; vol.sD = la.sD; vol.sH = la.sH; vol.sW = la.sW;
     const Sample sm = sample_coords(g, p, va, s, vol);
-    const int b = s / va.V;
+    const int b = blockIdx.z;
     const L* __restrict__ src = (const L*)la.data + (long long)b * la.sB;
-    const size_t plane = (size_t)g.Do * g.Ho * g.Wo;
+    const int plane = g.Do * g.Ho * g.Wo;      // C * plane < 2^31 (checked on the host): 32-bit channel offsets
     const size_t pix = ((size_t)p.i * g.Ho + p.j) * g.Wo + p.k;
     if (y_soft) {
         const Corners cn = corners_of(sm, vol);
@@ -64,7 +64,7 @@ onehot_fwd_kernel(LabArgs la, ViewArgs va, OutGeom g, float* __restrict__ y_soft
                 float acc = 0.0f;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) acc = __fadd_rn(acc, lab[k] == c ? w[k] : 0.0f);
-                dst[(size_t)c * plane] = acc;
+                dst[c * plane] = acc;
             }
         }
     }
@@ -74,7 +74,7 @@ onehot_fwd_kernel(LabArgs la, ViewArgs va, OutGeom g, float* __restrict__ y_soft
         const int ln = in ? load_label<L>(src + (long long)zn * la.sD + (long long)yn * la.sH + (long long)xn * la.sW) : -1;
         if (LABEL_OUT == 1) {
             int64_t* __restrict__ dl = (int64_t*)y_label + (size_t)s * la.C * plane + pix;
-            for (int c = 0; c < la.C; ++c) dl[(size_t)c * plane] = (ln == c) ? 1 : 0;
+            for (int c = 0; c < la.C; ++c) dl[c * plane] = (ln == c) ? 1 : 0;
         } else {
             ((uint8_t*)y_label)[(size_t)s * plane + pix] = in ? (uint8_t)ln : (uint8_t)0;
         }
@@ -84,7 +84,7 @@ onehot_fwd_kernel(LabArgs la, ViewArgs va, OutGeom g, float* __restrict__ y_soft
 template <typename L>
 __global__ void __launch_bounds__(NTHREADS, 3)
 onehot_bwd_kernel(LabArgs la, ViewArgs va, OutGeom g, const float* __restrict__ grad_out, double* __restrict__ ws_acc) {
-    const int s = blockIdx.y;
+    const int s = blockIdx.z * va.V + blockIdx.y;      // grid = (tiles, V, B): no integer division for the batch index
     float part[13];
 #pragma unroll
     for (int q = 0; q < 13; ++q) part[q] = 0.0f;
@@ -95,11 +95,11 @@ onehot_bwd_kernel(LabArgs la, ViewArgs va, OutGeom g, const float* __restrict__ 
         vol.sB = la.sB; vol.sC = 0; vol.sD = la.sD; vol.sH = la.sH; vol.sW = la.sW;
         const Sample sm = sample_coords(g, p, va, s, vol);
         const Corners cn = corners_of(sm, vol);
-        const int b = s / va.V;
+        const int b = blockIdx.z;
         const L* __restrict__ src = (const L*)la.data + (long long)b * la.sB;
         int lab[8];
         corner_labels<L>(src, cn, vol, lab);
-        const size_t plane = (size_t)g.Do * g.Ho * g.Wo;
+        const int plane = g.Do * g.Ho * g.Wo;      // C * plane < 2^31 (checked on the host): 32-bit channel offsets
         const float* __restrict__ go_p = grad_out + (size_t)s * la.C * plane + ((size_t)p.i * g.Ho + p.j) * g.Wo + p.k;
         float dot[8];
 #pragma unroll
@@ -108,7 +108,7 @@ onehot_bwd_kernel(LabArgs la, ViewArgs va, OutGeom g, const float* __restrict__ 
 #pragma unroll
         for (int c = 0; c < MAXC; ++c) {
             if (c < la.C) {
-                const float go = __ldg(go_p + (size_t)c * plane);
+                const float go = __ldg(go_p + c * plane);
                 gsum += go;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) dot[k] += (lab[k] == c) ? go : 0.0f;      // dot_k = grad_out[label_k]
@@ -133,7 +133,7 @@ static int make_lab_args(const afb_volume* lab, int num_classes, LabArgs& la) {
 template <typename L>
 static int launch_onehot_fwd(const LabArgs& la, const ViewArgs& a, const OutGeom& g, float* y_soft, void* y_label,
                              int label_out, cudaStream_t st) {
-    const dim3 grid = slice_grid(g, la.B * a.V);
+    const dim3 grid = slice_grid(g, la.B, a.V);
     switch (label_out) {
         case 0: onehot_fwd_kernel<L, 0><<<grid, NTHREADS, 0, st>>>(la, a, g, y_soft, y_label); break;
         case 1: onehot_fwd_kernel<L, 1><<<grid, NTHREADS, 0, st>>>(la, a, g, y_soft, y_label); break;
@@ -156,6 +156,7 @@ extern "C" int afb_slice_onehot_fwd(const afb_volume* labels, int num_classes, c
     if (rc != AFB_OK) return rc;
     if (!y_soft && label_out == 0) return AFB_EINVAL;
     if (label_out != 0 && !y_label) return AFB_EINVAL;
+    if ((long long)num_classes * Do * Ho * Wo >= 2147483647ll) return AFB_EUNSUPPORTED;     // 32-bit channel offsets
     const OutGeom g = make_geom(Do, Ho, Wo);
     cudaStream_t st = (cudaStream_t)stream;
     switch (labels->dtype) {
@@ -177,9 +178,10 @@ extern "C" int afb_slice_onehot_bwd(const afb_volume* labels, int num_classes, c
     if (rc != AFB_OK) return rc;
     if (!workspace || (!grad_y_soft && !grad_grid_affine) || !d_affine) return AFB_EINVAL;
     if (a.kind == AFB_AFFINE_PARAMS && !views->params) return AFB_EINVAL;
+    if ((long long)num_classes * Do * Ho * Wo >= 2147483647ll) return AFB_EUNSUPPORTED;     // 32-bit channel offsets
     const OutGeom g = make_geom(Do, Ho, Wo);
     const int S = la.B * a.V;
-    const dim3 grid = slice_grid(g, S);
+    const dim3 grid = slice_grid(g, la.B, a.V);
     double* acc = (double*)workspace;
     cudaStream_t st = (cudaStream_t)stream;
     if (grad_y_soft) {

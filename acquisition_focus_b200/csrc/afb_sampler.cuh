@@ -226,7 +226,8 @@ inline OutGeom make_geom(int Do, int Ho, int Wo) {
     return g;
 }
 
-inline dim3 slice_grid(const OutGeom& g, int S) { return dim3(((g.rows + TILE - 1) / TILE) * g.tiles_c, S); }
+// (tiles of one slice, views, volumes): slice s = blockIdx.z * V + blockIdx.y, volume b = blockIdx.z
+inline dim3 slice_grid(const OutGeom& g, int B, int V) { return dim3(((g.rows + TILE - 1) / TILE) * g.tiles_c, V, B); }
 
 
 }  // namespace afb

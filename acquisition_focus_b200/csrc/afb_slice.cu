@@ -26,14 +26,14 @@ template <typename T, int MODE>
 __global__ void __launch_bounds__(NTHREADS, 4)
 slice_fwd_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad_value, const float* pad_device,
                  T* __restrict__ out) {
-    const int s = blockIdx.y;
+    const int s = blockIdx.z * va.V + blockIdx.y;      // grid = (tiles, V, B): no integer division for the batch index
     const Pix p = pixel_of_thread(g);
     if (!p.valid) return;
     const Sample sm = sample_coords(g, p, va, s, vol);
-    const int b = s / va.V;
+    const int b = blockIdx.z;
     const T* __restrict__ src = (const T*)vol.data + (long long)b * vol.sB;
-    const size_t plane = (size_t)g.Do * g.Ho * g.Wo;
-    T* __restrict__ dst = out + (size_t)s * vol.C * plane + ((size_t)p.i * g.Ho + p.j) * g.Wo + p.k;
+    const int plane = g.Do * g.Ho * g.Wo;      // C * plane < 2^31 (checked on the host): 32-bit channel offsets
+    T* __restrict__ dst = out + (size_t)s * (size_t)(vol.C * plane) + ((p.i * g.Ho + p.j) * g.Wo + p.k);
 
     if (MODE == AFB_NEAREST) {
         // nearbyint = round half to even (cvt.rni), ATen grid_sampler_3d nearest
@@ -44,7 +44,7 @@ slice_fwd_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad_va
         for (int c = 0; c < vol.C; ++c) {
             T v = T(0);
             if (in) v = __ldg(src + (long long)c * vol.sC + off);
-            dst[(size_t)c * plane] = v;
+            dst[c * plane] = v;
         }
         return;
     }
@@ -61,7 +61,7 @@ slice_fwd_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad_va
 #pragma unroll
         for (int k = 0; k < 8; ++k)
             if (cn.in(k)) acc = __fadd_rn(acc, __fmul_rn(__fsub_rn(v[k], pad), cn.w(k)));
-        dst[(size_t)c * plane] = Store<T>::from_float(__fadd_rn(acc, pad));
+        dst[c * plane] = Store<T>::from_float(__fadd_rn(acc, pad));
     }
 }
 
@@ -73,14 +73,14 @@ template <typename T, int MODE, int VB, int BATCH = 8>
 __global__ void __launch_bounds__(NTHREADS, 3)
 slice_fwd_cl_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad_value, const float* pad_device,
                     T* __restrict__ out) {
-    const int s = blockIdx.y;
+    const int s = blockIdx.z * va.V + blockIdx.y;      // grid = (tiles, V, B): no integer division for the batch index
     const Pix p = pixel_of_thread(g);
     if (!p.valid) return;
     const Sample sm = sample_coords(g, p, va, s, vol);
-    const int b = s / va.V;
+    const int b = blockIdx.z;
     const T* __restrict__ src = (const T*)vol.data + (long long)b * vol.sB;
-    const size_t plane = (size_t)g.Do * g.Ho * g.Wo;
-    T* __restrict__ dst = out + (size_t)s * vol.C * plane + ((size_t)p.i * g.Ho + p.j) * g.Wo + p.k;
+    const int plane = g.Do * g.Ho * g.Wo;      // C * plane < 2^31 (checked on the host): 32-bit channel offsets
+    T* __restrict__ dst = out + (size_t)s * (size_t)(vol.C * plane) + ((p.i * g.Ho + p.j) * g.Wo + p.k);
     constexpr int N = VB / (int)sizeof(T);
 
     if (MODE == AFB_NEAREST) {
@@ -92,7 +92,7 @@ slice_fwd_cl_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad
             if (in) raw = gather_nc<VB>(src + off + c0);
             const T* e = reinterpret_cast<const T*>(raw.w);
 #pragma unroll
-            for (int q = 0; q < N; ++q) dst[(size_t)(c0 + q) * plane] = e[q];
+            for (int q = 0; q < N; ++q) dst[(c0 + q) * plane] = e[q];
         }
         return;
     }
@@ -123,7 +123,7 @@ slice_fwd_cl_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad
                     }
             }
 #pragma unroll
-            for (int q = 0; q < N; ++q) dst[(size_t)(c0 + q) * plane] = Store<T>::from_float(__fadd_rn(acc[q], pad));
+            for (int q = 0; q < N; ++q) dst[(c0 + q) * plane] = Store<T>::from_float(__fadd_rn(acc[q], pad));
         }
     }
 }
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
 slice_bwd_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad_value, const float* pad_device,
                  const float* __restrict__ grad_out, float* __restrict__ d_vol, float* __restrict__ d_pad,
                  double* __restrict__ ws_acc) {
-    const int s = blockIdx.y;
+    const int s = blockIdx.z * va.V + blockIdx.y;      // grid = (tiles, V, B): no integer division for the batch index
     float part[13];
 #pragma unroll
     for (int q = 0; q < 13; ++q) part[q] = 0.0f;
@@ -147,18 +147,18 @@ slice_bwd_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad_va
         const Sample sm = sample_coords(g, p, va, s, vol);
         const Corners cn = corners_of(sm, vol);
         const float pad = pad_of(pad_mode, pad_value, pad_device);
-        const int b = s / va.V;
+        const int b = blockIdx.z;
         const T* __restrict__ src = (const T*)vol.data + (long long)b * vol.sB;
         float* __restrict__ dv = d_vol ? d_vol + (long long)b * vol.sB : nullptr;
-        const size_t plane = (size_t)g.Do * g.Ho * g.Wo;
-        const float* __restrict__ go_p = grad_out + (size_t)s * vol.C * plane + ((size_t)p.i * g.Ho + p.j) * g.Wo + p.k;
+        const int plane = g.Do * g.Ho * g.Wo;      // C * plane < 2^31 (checked on the host): 32-bit channel offsets
+        const float* __restrict__ go_p = grad_out + (size_t)s * (size_t)(vol.C * plane) + ((p.i * g.Ho + p.j) * g.Wo + p.k);
         float dot[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) dot[k] = 0.0f;
         float gsum = 0.0f;
 #pragma unroll 2
         for (int c = 0; c < vol.C; ++c) {
-            const float go = __ldg(go_p + (size_t)c * plane);
+            const float go = __ldg(go_p + c * plane);
             const long long coff = (long long)c * vol.sC;
             gsum += go;
 #pragma unroll
@@ -183,7 +183,7 @@ slice_bwd_cl_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad
                     const float* __restrict__ grad_out, float* __restrict__ d_vol, float* __restrict__ d_pad,
                     double* __restrict__ ws_acc) {
     constexpr int N = VB / (int)sizeof(T);
-    const int s = blockIdx.y;
+    const int s = blockIdx.z * va.V + blockIdx.y;      // grid = (tiles, V, B): no integer division for the batch index
     float part[13];
 #pragma unroll
     for (int q = 0; q < 13; ++q) part[q] = 0.0f;
@@ -192,11 +192,11 @@ slice_bwd_cl_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad
         const Sample sm = sample_coords(g, p, va, s, vol);
         const Corners cn = corners_of(sm, vol);
         const float pad = pad_of(pad_mode, pad_value, pad_device);
-        const int b = s / va.V;
+        const int b = blockIdx.z;
         const T* __restrict__ src = (const T*)vol.data + (long long)b * vol.sB;
         float* __restrict__ dv = d_vol ? d_vol + (long long)b * vol.sB : nullptr;
-        const size_t plane = (size_t)g.Do * g.Ho * g.Wo;
-        const float* __restrict__ go_p = grad_out + (size_t)s * vol.C * plane + ((size_t)p.i * g.Ho + p.j) * g.Wo + p.k;
+        const int plane = g.Do * g.Ho * g.Wo;      // C * plane < 2^31 (checked on the host): 32-bit channel offsets
+        const float* __restrict__ go_p = grad_out + (size_t)s * (size_t)(vol.C * plane) + ((p.i * g.Ho + p.j) * g.Wo + p.k);
         float dot[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) dot[k] = 0.0f;
@@ -204,7 +204,7 @@ slice_bwd_cl_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad
         for (int c0 = 0; c0 < vol.C; c0 += N) {
             float go[N];
 #pragma unroll
-            for (int q = 0; q < N; ++q) { go[q] = __ldg(go_p + (size_t)(c0 + q) * plane); gsum += go[q]; }
+            for (int q = 0; q < N; ++q) { go[q] = __ldg(go_p + (c0 + q) * plane); gsum += go[q]; }
             // two batches of 4 corners (z0 plane, z1 plane): 4 vector gathers in flight per thread, half the registers
 #pragma unroll
             for (int h = 0; h < 8; h += BATCH) {
@@ -245,9 +245,9 @@ __global__ void __launch_bounds__(NTHREADS, 4)
 slice_pad_grad_kernel(VolArgs vol, ViewArgs va, OutGeom g, int ntiles, const float* __restrict__ grad_out,
                       float* __restrict__ d_pad) {
     __shared__ float red[NTHREADS / 32];
-    const int s = blockIdx.y;
-    const size_t plane = (size_t)g.Do * g.Ho * g.Wo;
-    const float* __restrict__ go_s = grad_out + (size_t)s * vol.C * plane;
+    const int s = blockIdx.z * va.V + blockIdx.y;      // grid = (tiles, V, B): no integer division for the batch index
+    const int plane = g.Do * g.Ho * g.Wo;      // C * plane < 2^31 (checked on the host): 32-bit channel offsets
+    const float* __restrict__ go_s = grad_out + (size_t)s * (size_t)(vol.C * plane);
     // phase 1: request every grad_out element of the PAD_TILES tiles (predicated, no control flow between the loads)
     Pix px[PAD_TILES];
     float gsum[PAD_TILES];
@@ -260,7 +260,7 @@ slice_pad_grad_kernel(VolArgs vol, ViewArgs va, OutGeom g, int ntiles, const flo
             px[u].valid = px[u].valid && tile < ntiles;
             const float* __restrict__ go_p = go_s + ((size_t)px[u].i * g.Ho + px[u].j) * g.Wo + px[u].k;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) v[u][c] = px[u].valid ? __ldg(go_p + (size_t)c * plane) : 0.0f;
+            for (int c = 0; c < 8; ++c) v[u][c] = px[u].valid ? __ldg(go_p + c * plane) : 0.0f;
         }
 #pragma unroll
         for (int u = 0; u < PAD_TILES; ++u) {
@@ -277,7 +277,7 @@ slice_pad_grad_kernel(VolArgs vol, ViewArgs va, OutGeom g, int ntiles, const flo
             const float* __restrict__ go_p = go_s + ((size_t)px[u].i * g.Ho + px[u].j) * g.Wo + px[u].k;
             gsum[u] = 0.0f;
             if (px[u].valid)
-                for (int c = 0; c < vol.C; ++c) gsum[u] += __ldg(go_p + (size_t)c * plane);
+                for (int c = 0; c < vol.C; ++c) gsum[u] += __ldg(go_p + c * plane);
         }
     }
     // phase 2: geometry (no memory traffic besides the 12 floats of the slice's grid affine)
@@ -314,6 +314,8 @@ static int make_args(const afb_volume* vol, const afb_views* views, int Do, int 
     if (vol->sD < 0 || vol->sH < 0 || vol->sW < 0) return AFB_EUNSUPPORTED;
     if ((long long)(vol->D + 2) * vol->sD + (long long)(vol->H + 2) * vol->sH + (long long)(vol->W + 2) * vol->sW >= 2147483647ll)
         return AFB_EUNSUPPORTED;
+    // channel offsets inside one slice's output are 32-bit in the kernels
+    if ((long long)vol->C * Do * Ho * Wo >= 2147483647ll) return AFB_EUNSUPPORTED;
     return make_view_args(views, vol->B, vol->D, vol->H, vol->W, Do, Ho, Wo, /*need_state=*/true, a);
 }
 
@@ -338,7 +340,7 @@ template <typename T>
 static int launch_fwd(const afb_volume* vol, const VolArgs& v, const ViewArgs& a, const OutGeom& g, int mode, int pad_mode,
                       float pad_value, const float* pad_device, void* out, cudaStream_t st) {
     const int S = v.B * a.V;
-    const dim3 grid = slice_grid(g, S);
+    const dim3 grid = slice_grid(g, v.B, a.V);
     const int vb = (mode == AFB_NEAREST || Widen<T>::is_float) ? channels_last_vec(vol, (int)sizeof(T), nullptr, 16) : 0;
     if (vb == 16 && mode == AFB_NEAREST) {
         slice_fwd_cl_kernel<T, AFB_NEAREST, 16><<<grid, NTHREADS, 0, st>>>(v, a, g, pad_mode, pad_value, pad_device, (T*)out);
@@ -355,7 +357,7 @@ static int launch_fwd(const afb_volume* vol, const VolArgs& v, const ViewArgs& a
 template <typename T>
 static int launch_bwd(const afb_volume* vol, const VolArgs& v, const ViewArgs& a, const OutGeom& g, int pad_mode, float pad_value,
                       const float* pad_device, const float* grad_out, float* d_vol, float* d_pad, double* acc, cudaStream_t st) {
-    const dim3 grid = slice_grid(g, v.B * a.V);
+    const dim3 grid = slice_grid(g, v.B, a.V);
     const int vb = channels_last_vec(vol, (int)sizeof(T), d_vol, 32);
     // measured on the B200 (384 slices, C = 8 fp32): LDG.256 x 4 corners in flight 0.689 ms, LDG.128 x 4: 0.718,
     // LDG.128 x 8 (the earlier kernel): 0.702
@@ -439,8 +441,8 @@ extern "C" int afb_slice_pad_grad(const afb_volume* vol, const afb_views* views,
     if (rc != AFB_OK) return rc;
     if (!grad_out || !d_pad) return AFB_EINVAL;
     const OutGeom g = make_geom(Do, Ho, Wo);
-    const dim3 tiles = slice_grid(g, v.B * a.V);
-    const dim3 grid((tiles.x + PAD_TILES - 1) / PAD_TILES, tiles.y);
+    const dim3 tiles = slice_grid(g, v.B, a.V);
+    const dim3 grid((tiles.x + PAD_TILES - 1) / PAD_TILES, tiles.y, tiles.z);
     slice_pad_grad_kernel<<<grid, NTHREADS, 0, (cudaStream_t)stream>>>(v, a, g, (int)tiles.x, grad_out, d_pad);
     return (int)cudaGetLastError();
 }
