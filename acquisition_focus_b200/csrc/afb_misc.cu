@@ -120,6 +120,24 @@ min_grad_fill_kernel(const T* __restrict__ vol, long long n, const float* __rest
         for (long long i = nvec * VEC + threadIdx.x; i < n; i += blockDim.x) d_vol[i] = (to_f<T>(vol[i]) == m) ? share : 0.0f;
 }
 
+// fp32 -> storage dtype over a dense block (dVolume of a bf16 / fp16 volume is accumulated in fp32 and handed back in the
+// volume's dtype and strides, like the reference's autograd would): 32 bytes in, 16 bytes out per thread per iteration.
+template <typename T>
+__global__ void __launch_bounds__(256)
+cast_from_f32_kernel(const float* __restrict__ src, T* __restrict__ dst, long long n) {
+    const long long nvec = n / 8;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(src) + 2 * i), b = __ldcs(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+        T o[8];
+        o[0] = Store<T>::from_float(a.x); o[1] = Store<T>::from_float(a.y); o[2] = Store<T>::from_float(a.z); o[3] = Store<T>::from_float(a.w);
+        o[4] = Store<T>::from_float(b.x); o[5] = Store<T>::from_float(b.y); o[6] = Store<T>::from_float(b.z); o[7] = Store<T>::from_float(b.w);
+        *reinterpret_cast<uint4*>(dst + 8 * i) = *reinterpret_cast<const uint4*>(o);
+    }
+    if (blockIdx.x == 0)
+        for (long long i = nvec * 8 + threadIdx.x; i < n; i += blockDim.x) dst[i] = Store<T>::from_float(src[i]);
+}
+
 // Measurement helper: read an (L2-resident) buffer `passes` times with 16-byte ld.global.cg loads; used by
 // bench.py to measure the L2 read-bandwidth denominator of the gather kernels' roofline on the same box.
 __global__ void __launch_bounds__(512)
@@ -239,6 +257,20 @@ extern "C" int afb_min_grad_fill(const void* vol, int dtype, int64_t n, const fl
         case AFB_F32: min_grad_fill_kernel<float><<<blocks, 256, 0, st>>>((const float*)vol, n, min_count, d_pad, d_vol); break;
         case AFB_BF16: min_grad_fill_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)vol, n, min_count, d_pad, d_vol); break;
         case AFB_F16: min_grad_fill_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)vol, n, min_count, d_pad, d_vol); break;
+        default: return AFB_EDTYPE;
+    }
+    return (int)cudaGetLastError();
+}
+
+extern "C" int afb_cast_from_f32(const float* src, void* dst, int dst_dtype, int64_t n, void* stream) {
+    if (!src || !dst || n <= 0) return AFB_EINVAL;
+    if (((uintptr_t)src & 15u) || ((uintptr_t)dst & 15u)) return AFB_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    long long want = (n / 8 + 255) / 256;
+    int blocks = (int)(want < 1 ? 1 : (want > 148 * 16 ? 148 * 16 : want));
+    switch (dst_dtype) {
+        case AFB_BF16: cast_from_f32_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(src, (__nv_bfloat16*)dst, n); break;
+        case AFB_F16: cast_from_f32_kernel<__half><<<blocks, 256, 0, st>>>(src, (__half*)dst, n); break;
         default: return AFB_EDTYPE;
     }
     return (int)cudaGetLastError();

@@ -275,7 +275,12 @@ class _SliceFn(torch.autograd.Function):
         if d_aff is not None and d_aff.dtype != ctx.in_dtype:
             d_aff = d_aff.to(ctx.in_dtype)
         if d_vol is not None and d_vol.dtype != volume.dtype:
-            d_vol = d_vol.to(volume.dtype)
+            # same dense block, same strides: one flat cast kernel instead of torch's strided element-wise copy
+            d_half = torch.empty_strided(volume.shape, volume.stride(), dtype=volume.dtype, device=dev)
+            with torch.cuda.device(dev):
+                L.check(lib.afb_cast_from_f32(L.ptr(d_vol), L.ptr(d_half), L.DTYPES[volume.dtype], volume.numel(), L.stream_ptr(dev)),
+                        "afb_cast_from_f32")
+            d_vol = d_half
         return (d_vol, d_aff) + none
 
 

@@ -124,6 +124,10 @@ int afb_volume_min_mask(const float* data, int64_t n_elements, float* out_min_co
 int afb_min_grad_fill_mask(const void* mask, int64_t n_elements, const float* min_count, const float* d_pad,
                            float* d_vol, void* stream);
 
+/* fp32 -> bf16 / fp16 (round to nearest even) over n contiguous elements: dVolume of a half-precision volume is
+ * accumulated in fp32 (afb_slice_bwd) and handed back in the volume's own dtype, as the reference's autograd does. */
+int afb_cast_from_f32(const float* src, void* dst, int dst_dtype, int64_t n_elements, void* stream);
+
 /* ---- one-hot materialisation (running/run_dl.py:261-264) fused with the min record ---------- */
 /* labels: n_voxels integers (label_dtype: AFB_U8/I16/I32/I64).  Writes, channels-last ([voxel][class], i.e. the strides
  * of `one_hot(label, C).permute(0,4,1,2,3)` and of its `.float()`):

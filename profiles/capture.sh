@@ -22,3 +22,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k 'regex:^(min_grad|slice_|view_|volume_min|onehot_|embed_)' --launch-skip 30 --launch-count 12 -f -o $out/prof_${tag}_step \
     python bench.py --volumes 16 --steps 2 --warmup 3 --no-cpu-baseline --no-breakdown --e2e-steps 1 > $out/ncu_full_$tag.log 2>&1; echo "ncu full rc=$?"
 fi
+if [ "$2" != "noncu" ] && [ -f bench_extra.py ]; then
+python bench_extra.py > $out/extra_$tag.jsonl 2> $out/extra_$tag.err; echo "bench_extra rc=$?"; tail -12 $out/extra_$tag.jsonl | cut -c1-260
+fi
