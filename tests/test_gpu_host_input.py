@@ -101,3 +101,26 @@ def test_upload_pipeline_matches_plain_path(afb, group):
     assert (soft1.grad - soft2.grad).abs().max().item() <= 1e-6 * soft1.grad.abs().max().item()
     assert torch.equal(soft1.grad == 0, soft2.grad == 0)
     assert (p1.grad - p2.grad).abs().max().item() <= 1e-6 * p1.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("n", [512 * 7, 4099, 2 ** 20 + 13])
+def test_record_of_arbitrary_fp32_volume(afb, n):
+    """[min, multiplicity] rebuilt from the record alone equals the direct pass, ties and ragged tails included."""
+    from acquisition_focus_b200 import functional as AF
+    gen = torch.Generator().manual_seed(n)
+    x = torch.randint(-3, 9, (n,), generator=gen).float().cuda()          # many ties at the minimum
+    direct = AF.volume_min(x, with_mask=True)
+    again = AF.min_count_from_record(direct._afb_mask, n)
+    assert torch.equal(direct, again) and direct[0].item() == -3.0 and direct[1].item() == float((x == -3).sum().item())
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_half_dvolume_cast_is_round_to_nearest_even(afb, dt):
+    """dVolume of a half-precision volume: fp32 accumulation, then ONE flat cast kernel == torch's .to(dtype), strides kept."""
+    import ctypes as C
+    from acquisition_focus_b200 import _lib as L
+    x = (torch.randn(3, 5, 7, 11, 8, generator=torch.Generator().manual_seed(9)) * 300).cuda()      # 9240 elements: ragged tail
+    x[0, 0, 0, 0, :4] = torch.tensor([65504.0, 1e-8, -0.0, 3.0e38]).cuda()
+    out = torch.empty_like(x, dtype=dt)
+    L.check(L.lib().afb_cast_from_f32(L.ptr(x), L.ptr(out), L.DTYPES[dt], x.numel(), L.stream_ptr(x.device)), "cast")
+    assert torch.equal(out, x.to(dt))
