@@ -172,7 +172,9 @@ def cfg5(afb, dev):
     init = torch.tensor([[1e-2, 0, 0, 0, 1e-2, 0, 0, 0, 0, 1.0]]).repeat(V, 1).to(dev)
     go = torch.randn(1, V, C, S, S, 1, device=dev)
     for dt in (torch.float32, torch.bfloat16):
-        soft = soft32.to(dt).requires_grad_(True)
+        # a fresh leaf per dtype: soft32.to(float32) would alias soft32, and once that requires grad the bf16 copy made from
+        # it becomes a NON-leaf whose backward also casts and accumulates into soft32.grad (0.74 ms of torch kernels)
+        soft = soft32.detach().to(dt, copy=True).requires_grad_(True)
 
         def ours():
             soft.grad = None; params.grad = None

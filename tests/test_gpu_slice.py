@@ -285,3 +285,39 @@ def test_identity_resample_and_linearity_fullsize(afb):
     a = afb.affine_grid_sample(vol[:, :1], th, (128, 128, 1)); b = afb.affine_grid_sample(vol[:, 1:], th, (128, 128, 1))
     c = afb.affine_grid_sample(2.0 * vol[:, :1] + vol[:, 1:], th, (128, 128, 1))
     close(c, 2.0 * a + b, 1e-5)
+
+
+def test_edge_shapes_vs_oracle(afb):
+    """Edge cases of the sampler boundary: a one-voxel-thin input (the W_in = 1 volumes of rotate_slice_to_min_principle,
+    learnable_transform.py:337-366), a single output location, and a slice lying completely outside the volume
+    (every corner masked: the output is the pad value, volume.min(), and MinBackward receives the whole gradient)."""
+    B = 2
+    nii = cases.synthetic.default_nifti_affine(B, 1.5)
+    P = cases.random_pre_affine(B, 33, 0.15)
+    # (1) thin input, 2-D -> 2-D resample, bilinear and nearest
+    thin = cases.randn((B, 3, 16, 20, 1), 31)
+    kw = dict(target_fov_mm=torch.tensor([20.0, 26.0, 1.5]), target_fov_vox=torch.tensor([12, 14, 1]))
+    ref = O.nifti_grid_sample(thin, nii, pre_grid_sample_affine=P, **kw)
+    out = afb.nifti_grid_sample(thin.cuda(), nii.cuda(), pre_grid_sample_affine=P.cuda(), **kw)
+    close(out[1], ref[1], 2e-6); close(out[0], ref[0], 2e-5); close(out[2], ref[2], 1e-9)
+    lab = cases.randint(0, 5, (B, 1, 16, 20, 1), 32)
+    refl = O.nifti_grid_sample(lab, nii, is_label=True, pre_grid_sample_affine=P, **kw)[0]
+    outl = afb.nifti_grid_sample(lab.cuda(), nii.cuda(), is_label=True, pre_grid_sample_affine=P.cuda(), **kw)[0]
+    assert outl.dtype == torch.int64 and (outl.cpu() != refl).float().mean().item() < 5e-3
+    # (2) one output location
+    vol = cases.randn((B, 2, 9, 10, 11), 34)
+    kw1 = dict(target_fov_mm=torch.tensor([1.5, 1.5, 1.5]), target_fov_vox=torch.tensor([1, 1, 1]))
+    close(afb.nifti_grid_sample(vol.cuda(), nii.cuda(), pre_grid_sample_affine=P.cuda(), **kw1)[0],
+          O.nifti_grid_sample(vol, nii, pre_grid_sample_affine=P, **kw1)[0], 2e-5)
+    # (3) slice shifted far outside the field of view
+    far = torch.eye(4)[None].repeat(B, 1, 1)
+    far[:, :3, 3] = torch.tensor([5.0, -4.0, 6.0])
+    kw2 = dict(target_fov_mm=torch.tensor([9.0, 9.0, 1.5]), target_fov_vox=torch.tensor([8, 8, 1]))
+    v1 = vol.clone().cuda().requires_grad_(True)
+    o = afb.nifti_grid_sample(v1, nii.cuda(), pre_grid_sample_affine=far.cuda(), **kw2)[0]
+    assert torch.equal(o, torch.full_like(o, vol.min().item()))
+    o.sum().backward()
+    v2 = vol.clone().requires_grad_(True)
+    O.nifti_grid_sample(v2, nii, pre_grid_sample_affine=far, **kw2)[0].sum().backward()
+    close(v1.grad, v2.grad, 1e-5)
+    assert v1.grad.flatten()[vol.flatten().argmin()].item() == float(o.numel())
