@@ -179,6 +179,81 @@ min_grad_fill_mask_kernel(const float* __restrict__ chunk_min, const unsigned sh
 }
 
 // ------------------------------------------------------------------------------------------------
+// 16-bit storage (bf16 / fp16 volumes, BASELINE configs[4]): same record, lane-major for 8-element vectors.
+// One chunk = 512 elements = two 16-byte loads per lane; bit 8j+q of lane l <-> element chunk*512 + j*256 + l*8 + q.
+// The fill writes fp32 dVolume (the backward accumulates in fp32) with one 32-byte store per lane (st.global.v8.f32).
+// ------------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float half_to_f(T v);
+template <> __device__ __forceinline__ float half_to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float half_to_f<__half>(__half v) { return __half2float(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(MM_THREADS)
+volume_min_mask_half_kernel(const T* __restrict__ data, long long n, long long n_chunks, float* __restrict__ chunk_min,
+                            unsigned short* __restrict__ bits, MinCountF* __restrict__ partial, unsigned* __restrict__ counter,
+                            float* __restrict__ out) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long warps = (long long)gridDim.x * (MM_THREADS / 32);
+    float gm = INFINITY, gc = 0.0f;
+    for (long long ch = (long long)blockIdx.x * (MM_THREADS / 32) + w; ch < n_chunks; ch += warps) {
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const long long e = ch * MM_CHUNK + j * 256 + lane * 8;
+            if (e + 7 < n) {
+                const uint4 raw = __ldcs(reinterpret_cast<const uint4*>(data + e));
+                const T* t = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[8 * j + q] = half_to_f<T>(t[q]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[8 * j + q] = e + q < n ? half_to_f<T>(data[e + q]) : INFINITY;
+            }
+        }
+        float c = INFINITY;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) c = fminf(c, v[q]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c = fminf(c, __shfl_xor_sync(0xffffffffu, c, o));
+        unsigned b = 0u;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) b |= (v[q] == c ? 1u : 0u) << q;
+        bits[ch * 32 + lane] = (unsigned short)b;
+        if (lane == 0) chunk_min[ch] = c;
+        mm_merge(gm, gc, c, (float)__popc(b));
+    }
+    mm_finish(gm, gc, partial, counter, out);
+}
+
+__global__ void __launch_bounds__(MM_THREADS)
+min_grad_fill_mask_half_kernel(const float* __restrict__ chunk_min, const unsigned short* __restrict__ bits, long long n,
+                               long long n_chunks, const float* __restrict__ min_count, const float* __restrict__ d_pad,
+                               float* __restrict__ d_vol) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long ch = (long long)blockIdx.x * (MM_THREADS / 32) + w;
+    if (ch >= n_chunks) return;
+    const float cm = __ldg(chunk_min + ch);
+    const unsigned braw = (unsigned)__ldg(bits + ch * 32 + lane);
+    const float m = __ldg(min_count), share = __ldg(d_pad) / __ldg(min_count + 1);
+    const unsigned b = cm == m ? braw : 0u;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const long long e = ch * MM_CHUNK + j * 256 + lane * 8;
+        float o[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o[q] = ((b >> (8 * j + q)) & 1u) ? share : 0.0f;
+        if (e + 7 < n) {
+            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(d_vol + e), "f"(o[0]), "f"(o[1]), "f"(o[2]),
+                         "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]) : "memory");
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (e + q < n) d_vol[e + q] = o[q];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // One-hot materialisation of running/run_dl.py:261-264 fused with the min record.
 //   label map (integer, one value per voxel) -> int64 one-hot [voxel][C] and/or fp32 one-hot [voxel][C]
 //   (channels-last in memory, i.e. exactly the strides of `one_hot(lab).permute(0,4,1,2,3)` and of its `.float()`).
@@ -360,5 +435,44 @@ extern "C" int afb_min_count_from_mask(const void* mask, int64_t n, float* out_m
     const long long wantb = (c + MM_THREADS / 32 - 1) / (MM_THREADS / 32);
     const int blocks = (int)(wantb < MM_BLOCKS ? wantb : MM_BLOCKS);
     mask_reduce_kernel<<<blocks, MM_THREADS, 0, st>>>(chunk_min, bits, c, partial, counter, out_min_count);
+    return (int)cudaGetLastError();
+}
+
+// bf16 / fp16 volumes: same record size and meaning, 8-element lane vectors (see volume_min_mask_half_kernel)
+extern "C" int afb_volume_min_mask_half(const void* data, int dtype, int64_t n, float* out_min_count, void* mask, void* workspace,
+                                        void* stream) {
+    if (!data || !out_min_count || !mask || !workspace || n <= 0) return AFB_EINVAL;
+    if (((uintptr_t)data & 15u) || ((uintptr_t)mask & 15u)) return AFB_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long c = mm_chunks(n);
+    float* chunk_min = (float*)mask;
+    unsigned short* bits = (unsigned short*)((char*)mask + ((c * (long long)sizeof(float) + 15) / 16) * 16);
+    unsigned* counter = (unsigned*)workspace;
+    MinCountF* partial = (MinCountF*)((char*)workspace + 16);
+    cudaError_t e = cudaMemsetAsync(counter, 0, 16, st);
+    if (e != cudaSuccess) return (int)e;
+    const long long wantb = (c + MM_THREADS / 32 - 1) / (MM_THREADS / 32);
+    const int blocks = (int)(wantb < MM_BLOCKS ? wantb : MM_BLOCKS);
+    if (dtype == AFB_BF16)
+        volume_min_mask_half_kernel<__nv_bfloat16><<<blocks, MM_THREADS, 0, st>>>((const __nv_bfloat16*)data, n, c, chunk_min, bits, partial,
+                                                                                  counter, out_min_count);
+    else if (dtype == AFB_F16)
+        volume_min_mask_half_kernel<__half><<<blocks, MM_THREADS, 0, st>>>((const __half*)data, n, c, chunk_min, bits, partial, counter,
+                                                                           out_min_count);
+    else
+        return AFB_EDTYPE;
+    return (int)cudaGetLastError();
+}
+
+extern "C" int afb_min_grad_fill_mask_half(const void* mask, int64_t n, const float* min_count, const float* d_pad, float* d_vol,
+                                           void* stream) {
+    if (!mask || !min_count || !d_pad || !d_vol || n <= 0) return AFB_EINVAL;
+    if (((uintptr_t)d_vol & 31u) || ((uintptr_t)mask & 15u)) return AFB_EINVAL;
+    const long long c = mm_chunks(n);
+    const float* chunk_min = (const float*)mask;
+    const unsigned short* bits = (const unsigned short*)((const char*)mask + ((c * (long long)sizeof(float) + 15) / 16) * 16);
+    const long long blocks = (c + MM_THREADS / 32 - 1) / (MM_THREADS / 32);
+    if (blocks > 2147483647ll) return AFB_EUNSUPPORTED;
+    min_grad_fill_mask_half_kernel<<<(unsigned)blocks, MM_THREADS, 0, (cudaStream_t)stream>>>(chunk_min, bits, n, c, min_count, d_pad, d_vol);
     return (int)cudaGetLastError();
 }

@@ -51,7 +51,7 @@ def _zeros_like_strided(t: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
 def volume_min(volume: torch.Tensor, with_mask: bool = False) -> torch.Tensor:
     """``volume.min()`` of nifti_utils.py:200 as a device tensor ``[min, multiplicity]`` (fp32).
 
-    ``with_mask`` (fp32 volumes): the same pass also leaves a 1-bit-per-voxel record of where the minimum sits
+    ``with_mask`` (fp32 / bf16 / fp16 volumes): the same pass also leaves a 1-bit-per-voxel record of where the minimum sits
     (``afb_volume_min_mask``), attached to the result as ``._afb_mask``; the backward then rebuilds MinBackward
     without re-reading the volume (half the HBM traffic of the dVolume fill).  The record refers to the memory
     layout of ``volume`` at call time."""
@@ -63,10 +63,14 @@ def volume_min(volume: torch.Tensor, with_mask: bool = False) -> torch.Tensor:
     with torch.cuda.device(dev):
         ws = torch.empty(int(lib.afb_volume_min_workspace_bytes()), dtype=torch.uint8, device=dev)
         out = torch.empty(2, dtype=torch.float32, device=dev)
-        if with_mask and volume.dtype == torch.float32:
+        if with_mask and volume.dtype in (torch.float32, torch.bfloat16, torch.float16):
             mask = torch.empty(int(lib.afb_min_mask_bytes(volume.numel())), dtype=torch.uint8, device=dev)
-            L.check(lib.afb_volume_min_mask(L.ptr(volume), volume.numel(), L.ptr(out), L.ptr(mask), L.ptr(ws),
-                                            L.stream_ptr(dev)), "afb_volume_min_mask")
+            if volume.dtype == torch.float32:
+                L.check(lib.afb_volume_min_mask(L.ptr(volume), volume.numel(), L.ptr(out), L.ptr(mask), L.ptr(ws),
+                                                L.stream_ptr(dev)), "afb_volume_min_mask")
+            else:       # same record, 8-element lane vectors: only afb_min_grad_fill_mask_half understands its bit order
+                L.check(lib.afb_volume_min_mask_half(L.ptr(volume), L.DTYPES[volume.dtype], volume.numel(), L.ptr(out), L.ptr(mask),
+                                                     L.ptr(ws), L.stream_ptr(dev)), "afb_volume_min_mask_half")
             out._afb_mask = mask
         else:
             L.check(lib.afb_volume_min(L.ptr(volume), L.DTYPES[volume.dtype], volume.numel(), L.ptr(out), L.ptr(ws),
@@ -260,8 +264,9 @@ class _SliceFn(torch.autograd.Function):
                             "afb_slice_pad_grad")
                     d_vol = torch.empty_strided(volume.shape, volume.stride(), dtype=torch.float32, device=dev)
                     if ctx.pad_mask is not None:        # 1-bit record left by the forward's min pass: no volume re-read
-                        L.check(lib.afb_min_grad_fill_mask(L.ptr(ctx.pad_mask), volume.numel(), L.ptr(pad_dev), L.ptr(d_pad),
-                                                           L.ptr(d_vol), st), "afb_min_grad_fill_mask")
+                        fill = lib.afb_min_grad_fill_mask if volume.dtype == torch.float32 else lib.afb_min_grad_fill_mask_half
+                        L.check(fill(L.ptr(ctx.pad_mask), volume.numel(), L.ptr(pad_dev), L.ptr(d_pad), L.ptr(d_vol), st),
+                                "afb_min_grad_fill_mask")
                     else:
                         L.check(lib.afb_min_grad_fill(L.ptr(volume), L.DTYPES[volume.dtype], volume.numel(), L.ptr(pad_dev),
                                                       L.ptr(d_pad), L.ptr(d_vol), st), "afb_min_grad_fill")

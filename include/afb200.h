@@ -124,6 +124,13 @@ int afb_volume_min_mask(const float* data, int64_t n_elements, float* out_min_co
 int afb_min_grad_fill_mask(const void* mask, int64_t n_elements, const float* min_count, const float* d_pad,
                            float* d_vol, void* stream);
 
+/* The same record for bf16 / fp16 volumes (dtype AFB_BF16 | AFB_F16): identical size (afb_min_mask_bytes) and meaning,
+ * lane vectors of 8 elements; the fill still writes fp32 dVolume (32-byte aligned).  afb_min_count_from_mask serves both. */
+int afb_volume_min_mask_half(const void* data, int dtype, int64_t n_elements, float* out_min_count, void* mask,
+                             void* workspace, void* stream);
+int afb_min_grad_fill_mask_half(const void* mask, int64_t n_elements, const float* min_count, const float* d_pad,
+                                float* d_vol, void* stream);
+
 /* fp32 -> bf16 / fp16 (round to nearest even) over n contiguous elements: dVolume of a half-precision volume is
  * accumulated in fp32 (afb_slice_bwd) and handed back in the volume's own dtype, as the reference's autograd does. */
 int afb_cast_from_f32(const float* src, void* dst, int dst_dtype, int64_t n_elements, void* stream);

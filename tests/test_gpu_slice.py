@@ -231,9 +231,11 @@ def test_min_shift_semantics_and_min_grad(afb):
     assert mc[0].item() == vol.min().item() and mc[1].item() == float((vol == vol.min()).sum())
 
 
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("n", [1, 7, 4096, 4097, 3 * 4096 + 1023, 1_000_003])
-def test_min_mask_record_equals_volume_reread(afb, n):
-    """afb_volume_min_mask + afb_min_grad_fill_mask (1-bit record, no volume re-read) == afb_volume_min + afb_min_grad_fill."""
+def test_min_mask_record_equals_volume_reread(afb, n, dt):
+    """afb_volume_min_mask[_half] + afb_min_grad_fill_mask[_half] (1-bit record, no volume re-read) == afb_volume_min +
+    afb_min_grad_fill, for fp32 and for 16-bit storage."""
     import ctypes as C
     from acquisition_focus_b200 import _lib as L
     from acquisition_focus_b200 import functional as AF
@@ -241,6 +243,7 @@ def test_min_mask_record_equals_volume_reread(afb, n):
     g = torch.Generator().manual_seed(n)
     vol = torch.randint(0, 5, (n,), generator=g).float() * 0.5 - 1.0        # many ties at the minimum, spread over chunks
     vol[torch.randint(0, n, (max(1, n // 50),), generator=g)] = -3.25
+    vol = vol.to(dt)                                                        # all values are exact in bf16 / fp16
     v = vol.cuda()
     plain, masked = AF.volume_min(v), AF.volume_min(v, with_mask=True)
     assert torch.equal(plain, masked) and hasattr(masked, "_afb_mask")
@@ -248,9 +251,11 @@ def test_min_mask_record_equals_volume_reread(afb, n):
     d_pad = torch.tensor([2.5], device="cuda")
     a = torch.full((n,), 7.0, device="cuda"); b = torch.full((n,), 7.0, device="cuda")
     st = L.stream_ptr(v.device)
-    L.check(lib.afb_min_grad_fill(L.ptr(v), L.F32, n, L.ptr(plain), L.ptr(d_pad), L.ptr(a), st), "fill")
-    L.check(lib.afb_min_grad_fill_mask(L.ptr(masked._afb_mask), n, L.ptr(masked), L.ptr(d_pad), L.ptr(b), st), "fill_mask")
+    L.check(lib.afb_min_grad_fill(L.ptr(v), L.DTYPES[dt], n, L.ptr(plain), L.ptr(d_pad), L.ptr(a), st), "fill")
+    fill = lib.afb_min_grad_fill_mask if dt == torch.float32 else lib.afb_min_grad_fill_mask_half
+    L.check(fill(L.ptr(masked._afb_mask), n, L.ptr(masked), L.ptr(d_pad), L.ptr(b), st), "fill_mask")
     assert torch.equal(a, b)
+    assert torch.equal(AF.min_count_from_record(masked._afb_mask, n), plain)
     want = (vol == vol.min()).float() * (2.5 / float((vol == vol.min()).sum()))
     assert torch.allclose(a.cpu(), want, rtol=1e-6, atol=0)
 
