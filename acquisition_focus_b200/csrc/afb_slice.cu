@@ -1,7 +1,7 @@
 // afb_slice.cu - slice / volume extraction (F.affine_grid + F.grid_sample of the reference,
 // utils/nifti_utils.py:182-203), forward and backward samplers.
 //
-// One launch covers all S = B*V slices: grid = (tiles per slice, S), 256 threads per CTA, one
+// One launch covers all S = B*V slices: grid = (tiles per slice, V, B), 256 threads per CTA, one
 // 16x16 tile of output locations per CTA.  Lanes of a warp cover an 8x4 patch (not 32x1) so that an
 // oblique plane touches few distinct 128-byte lines per load instruction.  The sampling grid is never
 // materialised: each thread rebuilds its coordinate from the per-slice grid affine (12 floats read from
@@ -11,8 +11,11 @@
 //   generic  - arbitrary element strides and storage dtype, loop over channels (image volumes, C = 1)
 //   channels-last (sC == 1) - what one_hot(...).permute(...) of running/run_dl.py:261-264 hands the
 //              sampler: the C channels of a voxel are contiguous, so a corner is one 16-byte load per
-//              4 fp32 channels (a full 32-byte sector for C = 8) and dVolume uses 16-byte vector
-//              reductions (red.global.add.v4.f32) - 4x fewer L2 atomic sectors than scalar REDs.
+//              4 fp32 channels in the forward, one 32-byte load (LDG.256, sm_100) per 8 channels in the
+//              backward, and dVolume uses 16-byte vector reductions (red.global.add.v4.f32) - 4x fewer
+//              L2 atomic sectors than scalar REDs.
+// Per-pixel instruction count matters here (the C = 1 and nearest kernels were issue-bound on coordinate and
+// address arithmetic): no integer or IEEE divisions on the common path, 32-bit offsets, see DESIGN.md section 5.
 #include <type_traits>
 
 #include "afb_sampler.cuh"
