@@ -401,22 +401,26 @@ def acquire_views(x_soft_label, x_label, x_image, nifti_affine, gpre, params, in
         y_label = torch.empty((B, V, xl.shape[1], Do, Ho, Wo), dtype=xl.dtype, device=dev) if has_l else None
         y_image = torch.empty((B, V, xi.shape[1], Do, Ho, Wo), dtype=xi.dtype, device=dev) if has_i else None
         ws_i = torch.empty(int(L.lib().afb_volume_min_workspace_bytes()) + 16, dtype=torch.uint8, device=dev) if has_i else None
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            if has_l:
-                _slice_forward_raw(xl, prepared[0], slice_fov_vox, L.NEAREST, L.PAD_ZERO, 0.0, None, out=y_label)
-            if has_i:
-                pm, pv, pd = L.PAD_ZERO, 0.0, None
-                if isinstance(image_pad, torch.Tensor):
-                    pm, pd = L.PAD_DEVICE, image_pad
-                elif image_pad == "global_min":
-                    pd = ws_i[:8].view(torch.float32)
-                    L.check(L.lib().afb_volume_min(L.ptr(xi), L.DTYPES[xi.dtype], xi.numel(), L.ptr(pd), L.ptr(ws_i[16:]),
-                                                   L.stream_ptr(dev)), "afb_volume_min")
-                    pm = L.PAD_DEVICE
-                elif image_pad != "zero":
-                    pm, pv = L.PAD_VALUE, float(image_pad)
-                _slice_forward_raw(xi, prepared[0], slice_fov_vox, L.BILINEAR, pm, pv, pd, out=y_image)
+        def side_work():
+            side.wait_event(forked)
+            with torch.cuda.stream(side):
+                if has_l:
+                    _slice_forward_raw(xl, prepared[0], slice_fov_vox, L.NEAREST, L.PAD_ZERO, 0.0, None, out=y_label)
+                if has_i:
+                    pm, pv, pd = L.PAD_ZERO, 0.0, None
+                    if isinstance(image_pad, torch.Tensor):
+                        pm, pd = L.PAD_DEVICE, image_pad
+                    elif image_pad == "global_min":
+                        pd = ws_i[:8].view(torch.float32)
+                        L.check(L.lib().afb_volume_min(L.ptr(xi), L.DTYPES[xi.dtype], xi.numel(), L.ptr(pd), L.ptr(ws_i[16:]),
+                                                       L.stream_ptr(dev)), "afb_volume_min")
+                        pm = L.PAD_DEVICE
+                    elif image_pad != "zero":
+                        pm, pv = L.PAD_VALUE, float(image_pad)
+                    _slice_forward_raw(xi, prepared[0], slice_fov_vox, L.BILINEAR, pm, pv, pd, out=y_image)
+
+        forked = main.record_event()                # everything the side stream needs exists at this point
+        side_work()                                 # (enqueueing the min pass first instead makes no difference: measured)
         y_soft, ga, nii, theta = _run_slice(x_soft_label, p, spec, slice_fov_vox, L.BILINEAR, soft_pad, prepared)
         main.wait_stream(side)
     else:
