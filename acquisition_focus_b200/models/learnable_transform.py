@@ -53,9 +53,9 @@ class AffineTransformModule(nn.Module):
         assert volume_fov_vox[0] == volume_fov_vox[1] == volume_fov_vox[2]
         assert optim_method in ["angle-axis", "normal-vector", "R6-vector"], \
             f"optim_method must be 'angle-axis', 'normal-vector' or 'R6-vector', not {optim_method}"
-        if align_corners or rotate_slice_to_min_principle:
-            raise NotImplementedError("align_corners / rotate_slice_to_min_principle are off in the reference "
-                                      "defaults and not part of the accelerated path")
+        if align_corners:
+            raise NotImplementedError("align_corners=True is never set by the reference's configs and is not part of "
+                                      "the accelerated path")
         self.optim_method = optim_method
         if optim_method == "R6-vector":                       # fused into the CUDA view prologue
             self.ap_space, self.optim_function = 6, compute_rotation_matrix_from_ortho6d
@@ -194,9 +194,71 @@ class AffineTransformModule(nn.Module):
             y_label = None if y_label is None else y_label[:, 0]
             y_image = None if y_image is None else y_image[:, 0]
             self.last_theta = theta
+        if self.rotate_slice_to_min_principle:                                           # reference :315-328
+            # quirk kept on purpose: the reference threads ONE NIfTI affine through the three calls, so the alignment is
+            # applied to it once per non-empty input (soft, label, image), not once
+            y_soft, align_affine, nii = rotate_slice_to_min_principle(y_soft, nii, is_label=False)
+            with torch.no_grad():
+                if y_label is not None:
+                    y_label, _, nii = rotate_slice_to_min_principle(y_label, nii, is_label=True, align_affine_override=align_affine)
+                if y_image is not None:
+                    y_image, _, nii = rotate_slice_to_min_principle(y_image, nii, is_label=False, align_affine_override=align_affine)
+            grid_affine = grid_affine @ align_affine
         self.last_grid_affine = grid_affine
         self.last_transformed_nifti_affine = nii
         return y_soft, y_label, y_image, grid_affine, nii
+
+
+def min_principle_align_affines(x_input: torch.Tensor) -> torch.Tensor:
+    """``[B,C,H,W,1]`` slices -> ``[B,4,4]`` torch-grid affines that turn each slice so that the axis of least inertia of its
+    foreground (``argmax`` over channels != 0) lies along the first in-plane axis (reference :346-355 with
+    ``utils/torch_sparse_tensor_utils.py:34-56,79-85`` and ``functional/clinical_cardiac_views.py:66-100``).
+
+    The second moments of the foreground are batched device reductions (fp64); the 3x3 eigenproblem and the frame are a few
+    dozen flops per sample and run on the host with ``torch.linalg.eig`` exactly as the reference does (one small D2H per
+    call), which also pins the sign convention of the eigenvectors to the reference's LAPACK path."""
+    assert x_input.dim() == 5 and x_input.shape[-1] == 1
+    B, _, H, W, _ = x_input.shape
+    dev = x_input.device
+    fg = (x_input.argmax(1)[..., 0] != 0).to(torch.float64)                              # [B,H,W]
+    hh = torch.arange(H, device=dev, dtype=torch.float64).view(1, H, 1)
+    ww = torch.arange(W, device=dev, dtype=torch.float64).view(1, 1, W)
+    n = fg.sum((1, 2))
+    ch, cw = (fg * hh).sum((1, 2)) / n, (fg * ww).sum((1, 2)) / n
+    dh, dw = hh - ch.view(B, 1, 1), ww - cw.view(B, 1, 1)
+    shh, sww, shw = (fg * dh * dh).sum((1, 2)), (fg * dw * dw).sum((1, 2)), (fg * dh * dw).sum((1, 2))
+    zero = torch.zeros_like(shh)
+    inertia = torch.stack([sww, -shw, zero, -shw, shh, zero, zero, zero, shh + sww], dim=1).view(B, 3, 3)
+    inertia, center = inertia.float().cpu(), torch.stack([ch, cw, torch.full_like(ch, 0.5)], dim=1).float().cpu()
+    shape = torch.tensor([H, W, 1], dtype=torch.float32)
+    out = torch.zeros(B, 4, 4)
+    for b in range(B):
+        eig = torch.linalg.eig(inertia[b])
+        main = eig.eigenvectors.real.T[eig.eigenvalues.real.argsort()][0]
+        main = main / torch.linalg.norm(main)
+        two = torch.linalg.cross(main, torch.tensor([0.0, 0.0, 1.0]))
+        two = two / torch.linalg.norm(two)
+        normal = torch.linalg.cross(main, two)
+        normal = normal / torch.linalg.norm(normal)
+        two = torch.linalg.cross(normal, main)
+        frame = torch.stack([two, main, normal], dim=0)                                  # pixel-space rows
+        out[b, :3, :3] = frame.flip(0, 1).T                                              # pixel -> torch-grid axis convention
+        out[b, :3, 3] = (2.0 * center[b] / shape - 1.0).flip(0)
+        out[b, 3, 3] = 1.0
+    return out.to(dev)
+
+
+def rotate_slice_to_min_principle(x_input, nii_affine, is_label=False, align_affine_override=None):
+    """Reference :337-366: re-align a one-voxel-thin slice volume ``[B,C,H,W,1]`` in-plane; same signature and return tuple
+    ``(y_output, b_align_affines, transformed_nii_affine)``.  The resample runs in the CUDA sampler (differentiable w.r.t.
+    ``x_input``); the alignment affine itself carries no gradient, as in the reference."""
+    assert x_input.shape[-1] == 1
+    if align_affine_override is None:
+        with torch.no_grad():
+            b_align_affines = min_principle_align_affines(x_input)
+    else:
+        b_align_affines = align_affine_override
+    return nifti_grid_sample(x_input, nii_affine, pre_grid_sample_affine=b_align_affines, is_label=is_label)
 
 
 class ATModulesContainer(nn.ModuleList):

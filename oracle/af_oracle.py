@@ -283,6 +283,56 @@ def atm_tail_forward(x_soft_label, x_label, x_image, nifti_affine, grid_affine_p
 
 
 # ----------------------------------------------------------------------------
+# a13  in-plane re-alignment of a slice                 models/learnable_transform.py:337-366
+#      (+ utils/torch_sparse_tensor_utils.py:34-56,79-85, functional/clinical_cardiac_views.py:66-100)
+# ----------------------------------------------------------------------------
+def min_principle_align_affine(label_slice: torch.Tensor) -> torch.Tensor:
+    """``label_slice[H,W,1]`` integer (argmax of one sample's slice) -> 4x4 torch-grid affine that turns the slice so that
+    the axis of least inertia of its foreground lies along the first in-plane axis.  Host arithmetic like the reference:
+    inertia tensor of the foreground index cloud (torch_sparse_tensor_utils.py:34-56), eigenvectors by ``torch.linalg.eig``
+    sorted by eigenvalue (:79-85), orthonormal frame (two, main, normal) through the centroid with its depth set to 0.5
+    (learnable_transform.py:346-353, clinical_cardiac_views.py:75-100), pixel -> grid convention (:66-71)."""
+    idx = label_slice.to_sparse()._indices()                                  # [3, n] foreground positions
+    center = idx.float().mean(1)
+    d = idx - center.view(3, 1)
+    r2 = torch.linalg.vector_norm(d, 2, dim=0) ** 2
+    inertia = torch.zeros(3, 3)
+    for i in range(3):
+        for j in range(3):
+            inertia[i, j] = (r2 * float(i == j) - d[i] * d[j]).sum()
+    center[-1] = 0.5
+    eig = torch.linalg.eig(inertia)
+    main = eig.eigenvectors.real.T[eig.eigenvalues.real.argsort()][0].clone()  # axis of least inertia
+    two = torch.linalg.cross(main, torch.tensor([0.0, 0.0, 1.0]))
+    main = main / torch.linalg.norm(main, 2)
+    two = two / torch.linalg.norm(two, 2)
+    normal = torch.linalg.cross(main, two)
+    normal = normal / torch.linalg.norm(normal, 2)
+    two = torch.linalg.cross(normal, main)
+    pix = torch.eye(4)
+    pix[:3, :3] = torch.stack([two, main, normal], dim=0)
+    pix[:3, -1] = center
+    out = pix.clone()
+    out[:3, :3] = out[:3, :3].flip(0, 1).T
+    out[:3, -1] = (2.0 * out[:3, -1] / torch.as_tensor(label_slice.shape) - 1.0).flip(0)
+    return out
+
+
+def rotate_slice_to_min_principle(x_input, nii_affine, is_label=False, align_affine_override=None):
+    """learnable_transform.py:337-366: per-sample alignment affine from ``argmax`` over the channels (unless overridden),
+    then a same-FOV resample of the one-voxel-thin slice volume with it."""
+    assert x_input.shape[-1] == 1
+    if align_affine_override is None:
+        aff = torch.zeros(x_input.shape[0], 4, 4).to(x_input.device)
+        with torch.no_grad():
+            for b, lbl in enumerate(x_input):
+                aff[b] = min_principle_align_affine(lbl.argmax(0))
+    else:
+        aff = align_affine_override
+    return nifti_grid_sample(x_input, nii_affine, pre_grid_sample_affine=aff, is_label=is_label)
+
+
+# ----------------------------------------------------------------------------
 # a6  clinical composition + augmentation              running/run_dl.py:208-234
 # ----------------------------------------------------------------------------
 def input_affine_for_view(base_affine, view_affine):

@@ -134,12 +134,12 @@ def gold_rotation_params(R):
     np.savez_compressed(os.path.join(GOLD, "rotation_params.npz"), **out)
 
 
-def _run_atm(R, case, optim_method="R6-vector", init_ap=None):
+def _run_atm(R, case, optim_method="R6-vector", init_ap=None, rotate=False):
     B, V, S = case["B"], case["V"], case["S"]
     res = []
     for v in range(V):
         atm = R.AffineTransformModule(8, case["volume_fov_mm"], case["volume_fov_vox"], case["slice_fov_mm"],
-                                      case["slice_fov_vox"], optim_method=optim_method,
+                                      case["slice_fov_vox"], optim_method=optim_method, rotate_slice_to_min_principle=rotate,
                                       offset_clip_value=case["offset_clip"], zoom_clip_value=case["zoom_clip"],
                                       view_id="p2CH")
         assert atm.vox_range == case["R"]
@@ -202,6 +202,20 @@ def gold_atm_other_params(R):
         np.savez_compressed(os.path.join(GOLD, "atm_s32_" + method.replace("-", "_") + ".npz"), **out)
 
 
+def gold_atm_rotate(R):
+    """a13: AffineTransformModule.forward with rotate_slice_to_min_principle=True (learnable_transform.py:315-328,337-366),
+    32^3, 2 views: aligned slices, the composed grid affine, the updated NIfTI affine and parameter gradients."""
+    from oracle import cases
+    case = cases.atm_case(32, 2, 2, seed=81)
+    res = _run_atm(R, case, rotate=True)
+    out = {"gpre": np.stack([_np(g) for g in case["gpre"]]), "params": np.stack([_np(p) for p in case["params"]])}
+    for v, r in enumerate(res):
+        out.update({f"ys{v}": _np(r["ys"]), f"yl{v}": _np(r["yl"]).astype(np.uint8), f"yi{v}": _np(r["yi"]),
+                    f"ga{v}": _np(r["ga"]), f"na{v}": _np(r["na"]), f"dparams{v}": _np(r["dparams"]),
+                    f"dsoft_sum_w{v}": _np(r["dsoft"].sum(-1))})
+    np.savez_compressed(os.path.join(GOLD, "atm_s32_rotate.npz"), **out)
+
+
 def gold_embed(R):
     from oracle import cases
     for tag, (S, c, V, B) in (("embed_s16", (16, 3, 2, 2)), ("embed_s8", (8, 4, 3, 2)), ("embed_s32", (32, 4, 6, 1))):
@@ -221,7 +235,8 @@ def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     R = load_reference()
     groups = {"views": write_view_affines, "r6": gold_r6, "slice_small": gold_slice_small, "slice_cfg1": gold_slice_cfg1,
-              "atm": gold_atm, "embed": gold_embed, "rotation_params": gold_rotation_params, "atm_other": gold_atm_other_params}
+              "atm": gold_atm, "embed": gold_embed, "rotation_params": gold_rotation_params, "atm_other": gold_atm_other_params,
+              "atm_rotate": gold_atm_rotate}
     for name in (sys.argv[1:] or list(groups)):          # python -m oracle.make_golden [group ...]
         groups[name](R)
     for f in sorted(os.listdir(GOLD)):

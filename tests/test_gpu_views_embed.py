@@ -167,6 +167,35 @@ def test_module_other_parameterisations_golden(afb, golden_dir, method, init_ap)
         close(atm.localization_net.p.grad, g[f"dparams{v}"], GRAD_REL, "dparams")
 
 
+def test_module_rotate_slice_to_min_principle_golden(afb, golden_dir):
+    """AffineTransformModule(rotate_slice_to_min_principle=True) against the reference's own outputs
+    (aligned soft / label / image slices, composed grid affine, NIfTI affine, parameter and volume gradients through BOTH
+    resamplings)."""
+    g = np.load(os.path.join(golden_dir, "atm_s32_rotate.npz"))
+    case = cases.atm_case(32, 2, 2, seed=81)
+
+    class Stub(torch.nn.Module):
+        def __init__(self, p):
+            super().__init__(); self.p = torch.nn.Parameter(p)
+        def forward(self, x):
+            return self.p
+    for v in range(2):
+        atm = afb.AffineTransformModule(8, case["volume_fov_mm"], case["volume_fov_vox"], case["slice_fov_mm"], case["slice_fov_vox"],
+                                        optim_method="R6-vector", offset_clip_value=case["offset_clip"], zoom_clip_value=0.0,
+                                        view_id="p2CH", rotate_slice_to_min_principle=True,
+                                        localization_net=Stub(case["params"][v].clone())).cuda()
+        soft = case["soft"].cuda().requires_grad_(True)
+        ys, yl, yi, ga, nii = atm(soft, case["label"].cuda(), case["image"].cuda(), case["nii"].cuda(), case["gpre"][v].cuda())
+        close(ga, g[f"ga{v}"], 5e-6, "grid affine")
+        close(nii, g[f"na{v}"], 1e-5, "nii affine")
+        close(ys, g[f"ys{v}"], 1e-4, "soft slice")            # two chained resamplings, alignment affine from fp32 moments
+        close(yi, g[f"yi{v}"], 1e-3, "image slice")
+        assert (yl.cpu().numpy().astype(np.uint8) != g[f"yl{v}"]).mean() < 5e-3
+        ((ys * cases.pattern(ys.shape, 1.0 + v).cuda()).sum() + (ga * cases.pattern(ga.shape, 2.0 + v).cuda()).sum()).backward()
+        close(atm.localization_net.p.grad, g[f"dparams{v}"], 5e-4, "dparams")
+        close(soft.grad.sum(-1), g[f"dsoft_sum_w{v}"], 5e-4, "dsoft")
+
+
 @pytest.mark.parametrize("tag,shape", [("embed_s16", (16, 3, 2, 2)), ("embed_s8", (8, 4, 3, 2)), ("embed_s32", (32, 4, 6, 1))])
 def test_embed_golden(afb, golden_dir, tag, shape):
     S, c, V, B = shape

@@ -76,4 +76,4 @@ def test_module_mirror_bookkeeping():
         afb.AffineTransformModule(8, fov, torch.tensor([128, 128, 128]), fov, torch.tensor([128, 128, 1]), optim_method="euler")
     with pytest.raises(NotImplementedError):
         afb.AffineTransformModule(8, fov, torch.tensor([128, 128, 128]), fov, torch.tensor([128, 128, 1]), optim_method="R6-vector",
-                                  rotate_slice_to_min_principle=True)
+                                  align_corners=True)

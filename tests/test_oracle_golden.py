@@ -136,3 +136,32 @@ def test_atm_other_parameterisations(golden_dir, method, init_ap):
         assert np.array_equal(yl.numpy().astype(np.uint8), g[f"yl{v}"]) and np.array_equal(yi.numpy(), g[f"yi{v}"])
         ((ys * cases.pattern(ys.shape, 1.0 + v)).sum() + (ga * cases.pattern(ga.shape, 2.0 + v)).sum()).backward()
         assert _close(params.grad.numpy(), g[f"dparams{v}"])
+
+
+# ---- in-plane re-alignment of the slices ---------------------------------------------------------------
+def test_atm_rotate_slice_to_min_principle(golden_dir):
+    """oracle restatement of learnable_transform.py:315-328,337-366 against the reference's outputs, and the product's
+    batched alignment-affine helper (device-agnostic torch + host eig) against the oracle's per-sample loop."""
+    from acquisition_focus_b200.models.learnable_transform import min_principle_align_affines
+    g = np.load(os.path.join(golden_dir, "atm_s32_rotate.npz"))
+    case = cases.atm_case(32, 2, 2, seed=81)
+    for v in range(2):
+        params = case["params"][v].clone().requires_grad_(True)
+        soft = case["soft"].clone().requires_grad_(True)
+        theta = O.view_theta(params, torch.tensor([[1e-2, 0, 0, 0, 1e-2, 0]]), torch.zeros(3), torch.ones(1, 1), case["offset_clip"], 0.0, 32)
+        ys, yl, yi, ga, na = O.atm_tail_forward(soft, case["label"], case["image"], case["nii"], case["gpre"][v], theta,
+                                                case["slice_fov_mm"], case["slice_fov_vox"])
+        helper = min_principle_align_affines(ys.detach())
+        loop = torch.stack([O.min_principle_align_affine(sl.argmax(0)) for sl in ys.detach()])
+        assert _close(helper.numpy(), loop.numpy(), rel=1e-6)
+        ys, align, na2 = O.rotate_slice_to_min_principle(ys, na, is_label=False)      # `align` is the resample's grid affine (:362)
+        with torch.no_grad():       # the reference threads one NIfTI affine through all three calls (:317-326)
+            yl, _, na2 = O.rotate_slice_to_min_principle(yl, na2, is_label=True, align_affine_override=align)
+            yi, _, na2 = O.rotate_slice_to_min_principle(yi, na2, is_label=False, align_affine_override=align)
+        ga = ga @ align
+        assert np.array_equal(ys.detach().numpy(), g[f"ys{v}"]) and np.array_equal(ga.detach().numpy(), g[f"ga{v}"])
+        assert np.array_equal(yl.numpy().astype(np.uint8), g[f"yl{v}"]) and np.array_equal(yi.numpy(), g[f"yi{v}"])
+        assert np.allclose(na2.detach().numpy(), g[f"na{v}"], rtol=1e-12, atol=1e-12)
+        ((ys * cases.pattern(ys.shape, 1.0 + v)).sum() + (ga * cases.pattern(ga.shape, 2.0 + v)).sum()).backward()
+        assert _close(params.grad.numpy(), g[f"dparams{v}"])
+        assert _close(soft.grad.sum(-1).numpy(), g[f"dsoft_sum_w{v}"])
