@@ -5,8 +5,10 @@ fused kernels: what the reference does with 14 ``nifti_grid_sample`` calls and ~
 
 Same signature and return tuple as the reference: ``(b_input[B, V*C, H, W], b_target[B, C, D, H, W] long,
 grid_affines: list[V] of [B,4,4])``; ``config`` is any object with the reference's attribute names
-(``config_dict.json``).  Only ``label_slice_type == 'from-gt'`` is on this path (``'from-segmented'`` needs the
-nnU-Net segmenter, out of scope).
+(``config_dict.json``).  ``label_slice_type == 'from-gt'`` with R6 view modules takes the fused all-views route;
+``'from-segmented'`` (the caller supplies ``segment_fn``, e.g. the reference's nnU-Net wrapper), the other rotation
+parameterisations and ``rotate_slice_to_min_principle`` go view by view through :func:`get_transformed`
+(``run_dl.py:146-204``), like the reference.
 """
 from __future__ import annotations
 
@@ -14,7 +16,7 @@ import torch
 import torch.nn.functional as F
 
 from ..synthetic import random_aug_affine
-from ..utils.nifti_utils import nifti_grid_sample
+from ..utils.nifti_utils import get_zooms, nifti_grid_sample
 
 
 def apply_affine_augmentation(affine_list, zoom_strength=0.1, offset_strength=0.1, rotation_strength=0.1, generator=None):
@@ -33,11 +35,42 @@ def get_input_affine_for_atm(atm, base_affine, b_view_affines):
     return base_affine.inverse() @ torch.as_tensor(b_view_affines[atm.view_id]).view(B, 4, 4).to(base_affine)
 
 
+def get_transformed(config, phase, label, soft_label, nifti_affine, grid_affine_pre_mlp, atm, image=None, segment_fn=None):
+    """run_dl.py:146-204, one view: ``atm`` slices the soft label / label / image volumes; for ``label_slice_type ==
+    'from-segmented'`` outside training the label slice is replaced by ``segment_fn(image_slice[B,C,1,D,H], zooms)`` (no
+    gradient any more, as in the reference); low-resolution slices are up-sampled to the hires FOV.
+    Returns ``(image_slc, soft_label_slc, grid_affine)``."""
+    img_is_invalid = image is None or image.dim() == 0
+    B, num_classes, D, H, W = label.shape
+    if img_is_invalid:
+        image = torch.zeros(B, 1, D, H, W, device=label.device)
+    soft_label_slc, label_slc, image_slc, grid_affine, atm_nii_affine = atm(
+        soft_label.view(B, num_classes, D, H, W), label.view(B, num_classes, D, H, W), image.view(B, 1, D, H, W),
+        nifti_affine, grid_affine_pre_mlp)
+    if getattr(config, "label_slice_type", "from-gt") == "from-segmented" and phase != "train":
+        assert not img_is_invalid and segment_fn is not None
+        with torch.no_grad():
+            pred_slc = segment_fn(image_slc.permute(0, 1, 4, 2, 3), get_zooms(atm_nii_affine)).long()      # B C D H 1 -> B C 1 D H
+            if pred_slc.shape[-1] != 1:
+                pred_slc = pred_slc[:, 0][..., None]                                                     # B 1 D H -> B D H 1
+            soft_label_slc = label_slc = F.one_hot(pred_slc, num_classes).permute(0, 4, 1, 2, 3).to(soft_label_slc)
+    if list(config.slice_fov_vox) != list(config.hires_fov_vox):
+        tgt = list(config.hires_fov_vox[:2]) + [1]
+        image_slc = F.interpolate(image_slc, size=tgt, mode="trilinear", align_corners=False)
+        soft_label_slc = F.interpolate(soft_label_slc, size=tgt, mode="trilinear", align_corners=False)
+    if img_is_invalid:
+        image_slc = torch.empty([])
+    return image_slc, soft_label_slc, grid_affine
+
+
+def _fused_route_ok(config, modules) -> bool:
+    return getattr(config, "label_slice_type", "from-gt") == "from-gt" and \
+        all(m.optim_method == "R6-vector" and not m.rotate_slice_to_min_principle for m in modules)
+
+
 def get_reconstruction_model_input(batch, phase, config, num_classes, atm_container, segment_fn=None, generator=None):
     """run_dl.py:238-329.  ``batch``: {'label' [B,D,H,W] int, 'image' [B,D,H,W] float, 'additional_data': {'nifti_affine'
     [B,4,4], 'gt_view_affines' | 'prescan_view_affines': {view name: [B,4,4], 'centroids': [B,4,4]}}}, CUDA tensors."""
-    if getattr(config, "label_slice_type", "from-gt") != "from-gt":
-        raise NotImplementedError("only label_slice_type='from-gt' is on the accelerated path")
     b_label, b_image = batch["label"], batch["image"]
     key = "gt_view_affines" if config.clinical_view_affine_type == "from-gt" else "prescan_view_affines"
     b_view_affines = batch["additional_data"][key]
@@ -61,6 +94,10 @@ def get_reconstruction_model_input(batch, phase, config, num_classes, atm_contai
         s = config.sample_augment_strength
         input_grid_affines = apply_affine_augmentation(input_grid_affines, rotation_strength=0.1 * s, zoom_strength=0.2 * s,
                                                        offset_strength=0.0, generator=generator)
+
+    if not _fused_route_ok(config, active):
+        return _per_view_route(config, phase, num_classes, active, input_grid_affines, b_label, b_image, nifti_affine, segment_fn,
+                               generator)
 
     # per-view MLP heads; gradient context per view as in :283-289
     mlp_outs = []
@@ -89,3 +126,30 @@ def get_reconstruction_model_input(batch, phase, config, num_classes, atm_contai
     assert b_input.dim() == 4
     b_target = F.one_hot(b_label.long(), num_classes).permute(0, 4, 1, 2, 3)          # :261-262 (a view, as in the reference)
     return b_input, b_target, output_grid_affines
+
+
+def _per_view_route(config, phase, num_classes, active, input_grid_affines, b_label, b_image, nifti_affine, segment_fn, generator):
+    """The reference's loop over views (run_dl.py:261-329) on the materialised one-hot volumes: used whenever a view cannot
+    take the fused all-views acquisition ('from-segmented', non-R6 parameterisations, in-plane re-alignment)."""
+    label = F.one_hot(b_label.long(), num_classes).permute(0, 4, 1, 2, 3)
+    soft = label.float()
+    B, C, D, H, W = label.shape
+    slices, grid_affines = [], []
+    for i, (atm, input_ga) in enumerate(zip(active, input_grid_affines)):
+        with_grad = config.view_optimization_mode == "opt-all" or \
+            (config.view_optimization_mode == "opt-current-fix-previous" and i == len(active) - 1)
+        with torch.enable_grad() if with_grad else torch.no_grad():
+            _, label_slc, output_ga = get_transformed(config, phase, label, soft, nifti_affine, input_ga, atm,
+                                                      image=b_image.view(B, 1, D, H, W), segment_fn=segment_fn)
+            if config.do_augment_recon_orientation and phase in config.aug_phases:
+                s = config.sample_augment_strength
+                output_ga = apply_affine_augmentation([output_ga], rotation_strength=0.1 * s, zoom_strength=0.2 * s,
+                                                      offset_strength=0.0, generator=generator)[0].to(nifti_affine)
+            slices.append(label_slc)
+            grid_affines.append(output_ga)
+    n_views, n_active = len(config.base_views), len(active)
+    slices = slices + [slices[-1]] * (n_views - n_active)
+    grid_affines = grid_affines + [grid_affines[-1]] * (n_views - n_active)
+    b_input = torch.cat(slices, dim=1).squeeze(-1)
+    assert b_input.dim() == 4
+    return b_input, label, grid_affines
