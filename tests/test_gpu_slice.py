@@ -57,6 +57,37 @@ def test_affine_grid_sample_bitwise_vs_aten_cpu(afb, shape, scale):
         assert out.dtype == dt and torch.equal(out.cpu().long(), ref)
 
 
+STRUCTURED = {
+    "identity": [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0]],                    # coordinates land exactly on voxel centres
+    "flip_x": [[-1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0]],
+    "swap_xy": [[0, 1, 0, 0], [1, 0, 0, 0], [0, 0, 1, 0]],
+    "swap_xz_flip": [[0, 0, -1, 0], [0, 1, 0, 0], [1, 0, 0, 0]],
+    "half_voxel_shift": [[1, 0, 0, 1.0 / 32], [0, 1, 0, -1.0 / 32], [0, 0, 1, 0]],   # exactly between two voxels: .5 ties
+    "zoom2": [[0.5, 0, 0, 0], [0, 0.5, 0, 0], [0, 0, 0.5, 0]],
+}
+
+
+@pytest.mark.parametrize("name", sorted(STRUCTURED))
+@pytest.mark.parametrize("sizes", [((32, 32, 32), (32, 32, 32)), ((32, 32, 32), (8, 8, 8)), ((32, 32, 32), (16, 16, 1)),
+                                   ((128, 128, 128), (32, 32, 1))])
+def test_structured_affines_tie_policy_bitwise_vs_aten_cpu(afb, name, sizes):
+    """Tie policy at the sampler boundary.  Axis-aligned views, exact down-sampling (128 -> 32: every coordinate is x.5) and
+    half-voxel shifts put sampling coordinates exactly on integers and halves, where `floor` / `nearbyint` (round half to
+    even) decide which voxel is read.  Given the same fp32 affine the kernels must take the same decisions as ATen on the
+    CPU: outputs are compared BITWISE, bilinear and nearest."""
+    (D, H, W), (Do, Ho, Wo) = sizes
+    th = torch.tensor(STRUCTURED[name], dtype=torch.float32)[None]
+    vol = cases.randn((1, 2, D, H, W), D + Do)
+    grid = F.affine_grid(th, [1, 2, Do, Ho, Wo], align_corners=False)
+    ref = F.grid_sample(vol, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+    out = afb.affine_grid_sample(vol.cuda(), th.cuda(), (Do, Ho, Wo), "bilinear")
+    assert torch.equal(out.cpu(), ref), f"bilinear: {(out.cpu() != ref).sum().item()} of {ref.numel()} differ"
+    lab = cases.randint(0, 100, (1, 2, D, H, W), D + Do + 1)
+    ref = F.grid_sample(lab.float(), grid, mode="nearest", padding_mode="zeros", align_corners=False).long()
+    out = afb.affine_grid_sample(lab.cuda(), th.cuda(), (Do, Ho, Wo), "nearest")
+    assert torch.equal(out.cpu(), ref), f"nearest: {(out.cpu() != ref).sum().item()} of {ref.numel()} differ"
+
+
 @pytest.mark.parametrize("shape", SHAPES[:3] + SHAPES[5:])
 def test_affine_grid_sample_backward(afb, shape):
     N, C, D, H, W, Do, Ho, Wo = shape
