@@ -6,7 +6,9 @@
 Every reference module on the training hot path that did ``from ...nifti_utils import
 nifti_grid_sample`` holds its own name binding (``models/learnable_transform.py:6``,
 ``running/run_dl.py:30``), so each one is patched, as are ``compute_rotation_matrix_from_ortho6d``
-(``models/learnable_transform.py:8``) and ``hybrid_unet.SkipConnector``.  The offline, host-side
+(``models/learnable_transform.py:8``), ``hybrid_unet.SkipConnector`` and, when ``running.run_dl`` is imported, its per-batch
+callers ``get_transformed`` / ``get_reconstruction_model_input`` (same signatures; with the reference's own
+``ATModulesContainer`` they take the view-by-view route, with this package's container the fused all-views one).  The offline, host-side
 callers (``datasets/base_dataset.py:19``, ``functional/clinical_cardiac_views.py:4``,
 ``utils/nnunetv2_utils.py:19``) are deliberately left on the reference's own code: they run once at
 dataset-preparation time on CPU tensors and are outside this path.
@@ -17,6 +19,7 @@ from __future__ import annotations
 import sys
 
 from .models.hybrid_unet import SkipConnector
+from .running.model_input import get_reconstruction_model_input, get_transformed
 from .utils.nifti_utils import nifti_grid_sample
 from .utils.transform_utils import compute_rotation_matrix_from_ortho6d
 
@@ -41,6 +44,13 @@ def install() -> list:
             _originals.setdefault((name, "compute_rotation_matrix_from_ortho6d"), mod.compute_rotation_matrix_from_ortho6d)
             mod.compute_rotation_matrix_from_ortho6d = compute_rotation_matrix_from_ortho6d
             done.append(f"{name}.compute_rotation_matrix_from_ortho6d")
+    mod = sys.modules.get("acquisition_focus.running.run_dl")          # the per-batch callers (run_dl.py:146-204, 238-329)
+    if mod is not None:
+        for attr, fn in (("get_transformed", get_transformed), ("get_reconstruction_model_input", get_reconstruction_model_input)):
+            if hasattr(mod, attr):
+                _originals.setdefault(("acquisition_focus.running.run_dl", attr), getattr(mod, attr))
+                setattr(mod, attr, fn)
+                done.append(f"acquisition_focus.running.run_dl.{attr}")
     mod = sys.modules.get("acquisition_focus.models.hybrid_unet")
     if mod is not None:
         _originals.setdefault(("acquisition_focus.models.hybrid_unet", "SkipConnector"), mod.SkipConnector)

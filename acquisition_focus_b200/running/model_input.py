@@ -63,9 +63,14 @@ def get_transformed(config, phase, label, soft_label, nifti_affine, grid_affine_
     return image_slc, soft_label_slc, grid_affine
 
 
-def _fused_route_ok(config, modules) -> bool:
+def _fused_route_ok(config, modules, atm_container=None) -> bool:
+    """The fused all-views acquisition needs this package's container (a reference ``ATModulesContainer`` whose modules call
+    the patched ``nifti_grid_sample`` still works, view by view), 'from-gt' label slices, R6 modules, no re-alignment."""
+    if atm_container is not None and not hasattr(atm_container, "acquire_from_labels"):
+        return False
     return getattr(config, "label_slice_type", "from-gt") == "from-gt" and \
-        all(m.optim_method == "R6-vector" and not m.rotate_slice_to_min_principle for m in modules)
+        all(getattr(m, "optim_method", None) == "R6-vector" and not getattr(m, "rotate_slice_to_min_principle", False)
+            for m in modules)
 
 
 def get_reconstruction_model_input(batch, phase, config, num_classes, atm_container, segment_fn=None, generator=None):
@@ -95,7 +100,7 @@ def get_reconstruction_model_input(batch, phase, config, num_classes, atm_contai
         input_grid_affines = apply_affine_augmentation(input_grid_affines, rotation_strength=0.1 * s, zoom_strength=0.2 * s,
                                                        offset_strength=0.0, generator=generator)
 
-    if not _fused_route_ok(config, active):
+    if not _fused_route_ok(config, active, atm_container):
         return _per_view_route(config, phase, num_classes, active, input_grid_affines, b_label, b_image, nifti_affine, segment_fn,
                                generator)
 

@@ -55,7 +55,7 @@ def test_per_view_route_equals_fused_route(monkeypatch):
     g_fused = [container[v].localization_net.p.grad.clone() for v in range(V)]
     for v in range(V):
         container[v].localization_net.p.grad = None
-    monkeypatch.setattr(MI, "_fused_route_ok", lambda *a: False)
+    monkeypatch.setattr(MI, "_fused_route_ok", lambda *a, **k: False)
     per_view = MI.get_reconstruction_model_input(batch, "train", cfg, C, container)
     (per_view[0] * go).sum().backward()
     assert torch.equal(per_view[0], fused[0]) and torch.equal(per_view[1], fused[1])

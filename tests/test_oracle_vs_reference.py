@@ -54,3 +54,22 @@ def test_skip_connector_matches_reference():
     a = R.SkipConnector(2)(case["x"], case["affines"])
     b = O.skip_connector(case["x"], case["affines"], 2)
     assert torch.equal(a, b)
+
+
+def test_install_patches_and_restores_the_reference_bindings():
+    """install() rebinds the hot-path names inside the imported reference modules, uninstall() puts the originals back."""
+    R = load_reference()
+    import acquisition_focus_b200.install as inst
+    import acquisition_focus_b200 as afb
+    lt, hu = R.learnable_transform, R.hybrid_unet
+    orig = (lt.nifti_grid_sample, lt.compute_rotation_matrix_from_ortho6d, hu.SkipConnector)
+    done = inst.install()
+    try:
+        assert lt.nifti_grid_sample is afb.nifti_grid_sample and hu.SkipConnector is afb.SkipConnector
+        assert lt.compute_rotation_matrix_from_ortho6d is afb.compute_rotation_matrix_from_ortho6d
+        assert len(done) >= 3
+        with pytest.raises(Exception):                         # patched functions take CUDA tensors only: no CPU fallback
+            lt.nifti_grid_sample(torch.zeros(1, 1, 4, 4, 4), torch.eye(4)[None].double())
+    finally:
+        inst.uninstall()
+    assert (lt.nifti_grid_sample, lt.compute_rotation_matrix_from_ortho6d, hu.SkipConnector) == orig
