@@ -62,6 +62,8 @@ _SIGNATURES = {
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "afb_slice_pad_grad": (C.c_int, [C.POINTER(AfbVolume), C.POINTER(AfbViews), C.c_int, C.c_int, C.c_int, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
+    "afb_slice_scatter": (C.c_int, [C.POINTER(AfbVolume), C.POINTER(AfbViews), C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]),
     "afb_min_grad_fill": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "afb_slice_fwd": (C.c_int, [C.POINTER(AfbVolume), C.POINTER(AfbViews), C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -238,6 +238,49 @@ slice_bwd_cl_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad
     bwd_reduce(s, part, pad_mode, d_pad, ws_acc);
 }
 
+// ------------------------------------------------------------------------------------------------
+// scatter-only half of the backward: dVolume += w_k * grad_out at the 8 corners.  Needs the geometry and grad_out only
+// (no volume gather), so the backward can be split: the dTheta half (slice_bwd* with d_vol == NULL: re-gather + dot
+// products + reduction) is independent of the MinBackward fill and runs on a side stream UNDER it, this half follows the
+// fill.  Issue-bound on the REDs: 16 x red.global.add.v4.f32 per pixel for C = 8.
+// ------------------------------------------------------------------------------------------------
+template <bool CL>
+__global__ void __launch_bounds__(NTHREADS, 4)
+slice_scatter_kernel(VolArgs vol, ViewArgs va, OutGeom g, const float* __restrict__ grad_out, float* __restrict__ d_vol) {
+    const int s = blockIdx.z * va.V + blockIdx.y;
+    const Pix p = pixel_of_thread(g);
+    if (!p.valid) return;
+    const Sample sm = sample_coords(g, p, va, s, vol);
+    const Corners cn = corners_of(sm, vol);
+    if (cn.inb == 0u) return;
+    float* __restrict__ dv = d_vol + (long long)blockIdx.z * vol.sB;
+    const int plane = g.Do * g.Ho * g.Wo;
+    const float* __restrict__ go_p = grad_out + (size_t)s * (size_t)(vol.C * plane) + ((p.i * g.Ho + p.j) * g.Wo + p.k);
+    float w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = cn.w(k);
+    if (CL) {
+        for (int c0 = 0; c0 < vol.C; c0 += 4) {
+            float go[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) go[q] = __ldg(go_p + (c0 + q) * plane);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (cn.in(k))
+                    atomicAdd(reinterpret_cast<float4*>(dv + cn.off(k, vol) + c0),
+                              make_float4(w[k] * go[0], w[k] * go[1], w[k] * go[2], w[k] * go[3]));
+        }
+    } else {
+        for (int c = 0; c < vol.C; ++c) {
+            const float go = __ldg(go_p + c * plane);
+            const long long coff = (long long)c * vol.sC;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (cn.in(k)) atomicAdd(dv + coff + cn.off(k, vol), w[k] * go);
+        }
+    }
+}
+
 // d(out)/d(pad) = sum go * (1 - sum of in-bounds weights): depends on geometry and grad_out only, so it can run
 // BEFORE the dVolume fill, which lets MinBackward be fused with the zero-fill (afb_min_grad_fill).
 // A pure stream over grad_out: each CTA covers PAD_TILES tiles with all their loads independent (enough bytes in
@@ -447,5 +490,22 @@ extern "C" int afb_slice_pad_grad(const afb_volume* vol, const afb_views* views,
     const dim3 tiles = slice_grid(g, v.B, a.V);
     const dim3 grid((tiles.x + PAD_TILES - 1) / PAD_TILES, tiles.y, tiles.z);
     slice_pad_grad_kernel<<<grid, NTHREADS, 0, (cudaStream_t)stream>>>(v, a, g, (int)tiles.x, grad_out, d_pad);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int afb_slice_scatter(const afb_volume* vol, const afb_views* views, int Do, int Ho, int Wo, const float* grad_out,
+                                 float* d_vol, void* stream) {
+    VolArgs v; ViewArgs a;
+    int rc = make_args(vol, views, Do, Ho, Wo, v, a);
+    if (rc != AFB_OK) return rc;
+    if (!grad_out || !d_vol) return AFB_EINVAL;
+    const OutGeom g = make_geom(Do, Ho, Wo);
+    const dim3 grid = slice_grid(g, v.B, a.V);
+    cudaStream_t st = (cudaStream_t)stream;
+    // dVolume is fp32 whatever the storage type of the volume; 16-byte vector REDs need 4-channel groups, 16-byte aligned
+    const bool cl = vol->sC == 1 && vol->C % 4 == 0 && ((uintptr_t)d_vol % 16) == 0 && vol->sW % 4 == 0 && vol->sH % 4 == 0 &&
+                    vol->sD % 4 == 0 && vol->sB % 4 == 0;
+    if (cl) slice_scatter_kernel<true><<<grid, NTHREADS, 0, st>>>(v, a, g, grad_out, d_vol);
+    else slice_scatter_kernel<false><<<grid, NTHREADS, 0, st>>>(v, a, g, grad_out, d_vol);
     return (int)cudaGetLastError();
 }

@@ -519,6 +519,8 @@ def kernel_breakdown(AF, dev, soft, label, image, nii, gpre, params, init, go, f
     out["slice_bwd(soft, dVolume+dTheta)"] = {"kernel": "slice_bwd_cl_kernel<float", "ms": t, "bytes": nS * Npix * NUM_CLASSES * (32 + 4 + 32), "bound": "l2"}
     t = _time(lambda: bwd(False), dev)
     out["slice_bwd(soft, dTheta only) [not in step]"] = {"kernel": "slice_bwd_cl_kernel<float", "ms": t, "bytes": nS * Npix * NUM_CLASSES * (32 + 4), "bound": "l2"}
+    t = _time(lambda: L.check(lib.afb_slice_scatter(C.byref(vd), C.byref(vs), S, S, 1, L.ptr(go), L.ptr(d_vol), st), "afb_slice_scatter"), dev)
+    out["slice_scatter(dVolume only: REDs, no gather) [not in step]"] = {"kernel": "slice_scatter_kernel<", "ms": t, "bytes": nS * Npix * NUM_CLASSES * (4 + 32), "bound": "l2"}
     for k, v in out.items():
         v["gbs"] = v["bytes"] / (v["ms"] * 1e-3) / 1e9
     return out, l2_gbs

@@ -194,6 +194,13 @@ int afb_slice_bwd(const afb_volume* vol, const afb_views* views, int Do, int Ho,
 int afb_slice_pad_grad(const afb_volume* vol, const afb_views* views, int Do, int Ho, int Wo,
                        const float* grad_out, float* d_pad, void* stream);
 
+/* Scatter-only half of the backward: d_vol (fp32, strides of `vol`, already filled) += w_k * grad_out at the 8 corners of
+ * every output location.  With it the backward splits into  afb_slice_bwd(d_vol = NULL)  (re-gather, dTheta reduction and
+ * chain: independent of the MinBackward fill, can run on another stream under it)  and  afb_slice_scatter  after the fill;
+ * together they give exactly what afb_slice_bwd with d_vol does. */
+int afb_slice_scatter(const afb_volume* vol, const afb_views* views, int Do, int Ho, int Wo, const float* grad_out,
+                      float* d_vol, void* stream);
+
 /* d_vol[i] = (vol[i] == min) ? d_pad / count : 0   for all i (initialises d_vol; replaces memset + afb_min_grad) */
 int afb_min_grad_fill(const void* vol, int dtype, int64_t n_elements, const float* min_count,
                       const float* d_pad, float* d_vol, void* stream);
