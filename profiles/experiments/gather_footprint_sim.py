@@ -33,6 +33,40 @@ fov_mm_out = torch.tensor([192.0, 192.0, 1.5], dtype=torch.float64)
 fov_out = torch.tensor([S, S, 1], dtype=torch.float64)
 
 lines_per_req, sectors_per_req, uniq_vox, rows_per_tile, run_vox, fully_out = [], [], [], [], [], 0
+ana_vox, ana_rows, ana_missed = [], [], 0      # analytic row runs (what a kernel can compute without looking at the pixels)
+
+
+def analytic_runs(ixt, iyt, izt):
+    """Row runs of one 16x16 tile from its affine geometry alone.  Within the slicing plane x is a linear function of (y, z):
+    x = g + a*y + b*z, so the voxels of row (y, z) that any pixel's 2x2x2 corner block can touch lie in
+    [x_c - (|a|+|b|) - 1, x_c + (|a|+|b|) + 1] with x_c = g + a*y + b*z (|iy - y| <= 1, |iz - z| <= 1), clipped to the tile's own
+    x-range; rows whose (y, z) box maps outside the tile's pixel rectangle are skipped.  Conservative by construction."""
+    p00 = np.array([ixt[0, 0], iyt[0, 0], izt[0, 0]], dtype=np.float64)
+    u = (np.array([ixt[15, 0], iyt[15, 0], izt[15, 0]]) - p00) / 15.0
+    v = (np.array([ixt[0, 15], iyt[0, 15], izt[0, 15]]) - p00) / 15.0
+    xt_lo, xt_hi = int(np.floor(ixt.min())), int(np.floor(ixt.max())) + 1
+    ylo, yhi = int(np.floor(iyt.min() - 1e-3)), int(np.floor(iyt.max() + 1e-3)) + 1
+    zlo, zhi = int(np.floor(izt.min() - 1e-3)), int(np.floor(izt.max() + 1e-3)) + 1
+    det = u[1] * v[2] - v[1] * u[2]
+    runs = {}
+    for z in range(max(zlo, 0), min(zhi, S - 1) + 1):
+        for y in range(max(ylo, 0), min(yhi, S - 1) + 1):
+            lo, hi = xt_lo, xt_hi
+            if abs(det) > 1e-3:
+                minv = np.array([[v[2], -v[1]], [-u[2], u[1]]]) / det          # (iy - Y0, iz - Z0) -> (row idx, col idx)
+                d = np.array([y - p00[1], z - p00[2]])
+                ab = minv @ d
+                slack = np.abs(minv).sum(1) * 1.001 + 1e-3
+                if ab[0] + slack[0] < 0 or ab[0] - slack[0] > 15 or ab[1] + slack[1] < 0 or ab[1] - slack[1] > 15:
+                    continue                                                    # no pixel of this tile can touch the row
+                coef = np.array([u[0], v[0]]) @ minv                            # dx/d(iy), dx/d(iz) inside the plane
+                xc = p00[0] + coef @ d
+                half = np.abs(coef).sum() * 1.001 + 1e-3
+                lo, hi = max(lo, int(np.floor(xc - half))), min(hi, int(np.floor(xc + half)) + 1)
+            lo, hi = max(lo, 0), min(hi, S - 1)
+            if hi >= lo:
+                runs[(z, y)] = (lo, hi)
+    return runs
 for b in range(nv):
     for v in range(V):
         theta = O.view_theta(h["params"][b:b + 1, v], h["init"][v:v + 1, :6], h["init"][v, 6:9], h["init"][v:v + 1, 9:],
@@ -78,6 +112,10 @@ for b in range(nv):
                 uniq_vox.append(len(vox))
                 rows_per_tile.append(len(rows))
                 run_vox.append(sum(hi - lo + 1 for lo, hi in rows.values()))
+                ar = analytic_runs(ix[sl].numpy(), iy[sl].numpy(), iz[sl].numpy())
+                ana_vox.append(sum(hi - lo + 1 for lo, hi in ar.values()))
+                ana_rows.append(len(ar))
+                ana_missed += sum(1 for (cc, bb, a) in vox if (cc, bb) not in ar or not (ar[(cc, bb)][0] <= a <= ar[(cc, bb)][1]))
 
 
 def q(a):
@@ -92,3 +130,8 @@ print("per 16x16 tile: unique voxels touched:   ", q(uniq_vox), f"  (= {np.mean(
 print("                (y,z) rows:              ", q(rows_per_tile))
 print("                row-run staging, voxels: ", q(run_vox), f"  (= {np.mean(run_vox) * 32 / 1024:.1f} KiB mean, {np.max(run_vox) * 32 / 1024:.1f} KiB max)")
 print(f"                staged / unique = {np.sum(run_vox) / np.sum(uniq_vox):.2f};  tiles over 40 KiB: {np.mean(np.asarray(run_vox) * 32 > 40 * 1024) * 100:.1f} %")
+print("analytic row runs (from the tile's affine geometry only, no per-pixel pass):")
+print("                rows:                    ", q(ana_rows))
+print("                staged voxels:           ", q(ana_vox), f"  (= {np.mean(ana_vox) * 32 / 1024:.1f} KiB mean, {np.max(ana_vox) * 32 / 1024:.1f} KiB max)")
+print(f"                staged / unique = {np.sum(ana_vox) / np.sum(uniq_vox):.2f};  needed voxels NOT covered (would take the global-load fallback): "
+      f"{ana_missed} of {int(np.sum(uniq_vox))};  tiles over 48 KiB: {np.mean(np.asarray(ana_vox) * 32 > 48 * 1024) * 100:.1f} %")
