@@ -50,3 +50,32 @@ def test_backward_tolerance(shape):
     assert np.abs(dg - g.grad.numpy()).max() <= 1e-5 * g.grad.abs().max().item()
     dth = A.affine_grid_3d_backward(g.grad.numpy())
     assert np.abs(dth - th.grad.numpy()).max() <= 1e-5 * th.grad.abs().max().item()
+
+
+STRUCTURED = {
+    "identity": [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0]],
+    "flip_x": [[-1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0]],
+    "swap_xz_flip": [[0, 0, -1, 0], [0, 1, 0, 0], [1, 0, 0, 0]],
+    "half_voxel_shift": [[1, 0, 0, 1.0 / 32], [0, 1, 0, -1.0 / 32], [0, 0, 1, 0]],
+    "zoom2": [[0.5, 0, 0, 0], [0, 0.5, 0, 0], [0, 0, 0.5, 0]],
+}
+
+
+@pytest.mark.parametrize("name", sorted(STRUCTURED))
+@pytest.mark.parametrize("sizes", [((32, 32, 32), (32, 32, 32)), ((32, 32, 32), (8, 8, 8)), ((64, 64, 64), (16, 16, 1))])
+def test_structured_affines_tie_policy_bitwise(name, sizes):
+    """Coordinates exactly on integers / halves (axis-aligned views, exact down-sampling, half-voxel shifts): the numpy
+    restatement takes the same floor / round-half-even decisions as ATen (the CUDA kernels are checked the same way in
+    tests/test_gpu_slice.py)."""
+    (D, H, W), (Do, Ho, Wo) = sizes
+    th = torch.tensor(STRUCTURED[name], dtype=torch.float32)[None]
+    torch.manual_seed(D + Do)
+    vol = torch.randn(1, 2, D, H, W)
+    g = F.affine_grid(th, [1, 2, Do, Ho, Wo], align_corners=False)
+    gn = A.affine_grid_3d(th.numpy(), (Do, Ho, Wo))
+    assert np.array_equal(g.numpy(), gn)
+    o = F.grid_sample(vol, g, mode="bilinear", padding_mode="zeros", align_corners=False).numpy()
+    assert np.array_equal(o, A.grid_sample_3d(vol.numpy(), gn, "bilinear"))
+    lab = torch.randint(0, 50, (1, 2, D, H, W))
+    o = F.grid_sample(lab.float(), g, mode="nearest", padding_mode="zeros", align_corners=False).long().numpy()
+    assert np.array_equal(o, A.grid_sample_3d(lab.numpy(), gn, "nearest"))
