@@ -19,10 +19,9 @@ import torch
 import torch.nn as nn
 
 from .. import functional as AF
-from ..synthetic import random_aug_affine
 from ..utils.nifti_utils import nifti_grid_sample
 from ..utils.transform_utils import (angle_axis_to_rotation_matrix, compute_rotation_matrix_from_ortho6d,
-                                     normal_to_rotation_matrix)
+                                     get_random_affine, normal_to_rotation_matrix)
 
 
 class DefaultLocalizationNet(nn.Module):
@@ -87,8 +86,7 @@ class AffineTransformModule(nn.Module):
         self.last_theta = None
         self.last_grid_affine = None
         self.last_transformed_nifti_affine = None
-        self.random_grid_affine = random_aug_affine(torch.Generator().manual_seed(torch.seed() % (2 ** 31)),
-                                                    rotation_strength=4.0, zoom_strength=0.0)[None]
+        self.random_grid_affine = get_random_affine(rotation_strength=4.0, zoom_strength=0.0)[None]   # global RNG (:136)
 
     # -- same small API as the reference ---------------------------------------------------------
     def set_init_theta_ap(self, init_theta_ap):
@@ -293,12 +291,25 @@ class ATModulesContainer(nn.ModuleList):
     def get_active_view_modules(self):
         return [m for m, a in zip(self, self.get_active_views()) if a]
 
+    def get_next_non_optimized_view_module(self):
+        """reference :407-411 (used by the training loop, running/run_dl.py:117,125,416)."""
+        next_idx = self.__get_next_non_optimized_idx__()
+        if next_idx is not None:
+            return self[next_idx]
+        return None
+
+    def __get_next_non_optimized_idx__(self):
+        if False in self.is_optimized:
+            return (self.is_optimized == False).nonzero()[0]          # noqa: E712  (tensor comparison, as in the reference)
+        return None
+
     def acquire(self, x_soft_label, x_label, x_image, nifti_affine, view_pre_affines, mlp_outs: Optional[list] = None):
         """All views in ONE launch per volume kind.  ``view_pre_affines``: list (len V) of ``[B,4,4]``;
         ``mlp_outs``: optional list of ``[B, 6+3R+1]`` (else each module's LocalizationNet is run).
         Returns ``(y_soft[B,V,C,H,W,1], y_label, y_image, grid_affines[B,V,4,4], nii[B,V,4,4])``."""
         atms = list(self)
         assert all(m.optim_method == "R6-vector" for m in atms), "the fused all-views acquisition takes R6 parameters"
+        assert all(m.use_affine_theta for m in atms), "use_affine_theta=False (init affines only) goes view by view"
         dev = x_soft_label.device
         gpre = torch.stack([g.to(dev, torch.float32) for g in view_pre_affines], dim=1)
         if mlp_outs is None:
@@ -321,6 +332,7 @@ class ATModulesContainer(nn.ModuleList):
         all the reference's training step consumes.  ``modules``: the active view modules (default: all)."""
         atms = list(self) if modules is None else list(modules)
         assert all(m.optim_method == "R6-vector" for m in atms), "the fused all-views acquisition takes R6 parameters"
+        assert all(m.use_affine_theta for m in atms), "use_affine_theta=False (init affines only) goes view by view"
         dev = label_map.device
         gpre = torch.stack([g.to(dev, torch.float32) for g in view_pre_affines], dim=1)
         if mlp_outs is None:

@@ -15,15 +15,17 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 
-from ..synthetic import random_aug_affine
 from ..utils.nifti_utils import get_zooms, nifti_grid_sample
+from ..utils.transform_utils import get_random_affine
 
 
 def apply_affine_augmentation(affine_list, zoom_strength=0.1, offset_strength=0.1, rotation_strength=0.1, generator=None):
-    """run_dl.py:208-223: right-multiply every affine of the list by ONE random affine per batch element (host RNG)."""
-    gen = generator if generator is not None else torch.Generator().manual_seed(int(torch.randint(0, 2 ** 31 - 1, (1,))))
+    """run_dl.py:208-223: right-multiply every affine of the list by ONE random affine per batch element.  Host RNG with the
+    reference's draw sequence: with ``generator=None`` (the global torch RNG the reference uses) a seeded run reproduces the
+    reference's augmentation affines bit for bit (golden ``model_input_s32.npz``)."""
     B = affine_list[0].shape[0]
-    b_affine = torch.stack([random_aug_affine(gen, rotation_strength, zoom_strength, offset_strength) for _ in range(B)])
+    b_affine = torch.stack([get_random_affine(rotation_strength, zoom_strength, offset_strength, generator=generator)
+                            for _ in range(B)])
     return [a @ b_affine.to(a) for a in affine_list]
 
 
@@ -68,9 +70,14 @@ def _fused_route_ok(config, modules, atm_container=None) -> bool:
     the patched ``nifti_grid_sample`` still works, view by view), 'from-gt' label slices, R6 modules, no re-alignment."""
     if atm_container is not None and not hasattr(atm_container, "acquire_from_labels"):
         return False
+    if not getattr(config, "use_affine_theta", True) or not all(getattr(m, "use_affine_theta", True) for m in modules):
+        return False          # 'ref' stage (running/stages.py:76-82): init affines only, the MLP heads are not applied
     return getattr(config, "label_slice_type", "from-gt") == "from-gt" and \
         all(getattr(m, "optim_method", None) == "R6-vector" and not getattr(m, "rotate_slice_to_min_principle", False)
             for m in modules)
+
+
+_ONEHOT_MAX_CLASSES = 16      # afb_onehot.cu MAXC: channels the one-hot-from-index kernels hold in registers
 
 
 def get_reconstruction_model_input(batch, phase, config, num_classes, atm_container, segment_fn=None, generator=None):
@@ -100,7 +107,9 @@ def get_reconstruction_model_input(batch, phase, config, num_classes, atm_contai
         input_grid_affines = apply_affine_augmentation(input_grid_affines, rotation_strength=0.1 * s, zoom_strength=0.2 * s,
                                                        offset_strength=0.0, generator=generator)
 
-    if not _fused_route_ok(config, active, atm_container):
+    # the one-hot-from-index kernels take 2..16 classes (pad value 0 = min of a one-hot needs C >= 2) and <= 65535 slices
+    fused = _fused_route_ok(config, active, atm_container) and 2 <= num_classes <= _ONEHOT_MAX_CLASSES and B * len(active) <= 65535
+    if not fused:
         return _per_view_route(config, phase, num_classes, active, input_grid_affines, b_label, b_image, nifti_affine, segment_fn,
                                generator)
 

@@ -13,6 +13,30 @@ import torch
 from .. import functional as AF
 
 
+def get_random_affine(rotation_strength: float = 0.2, zoom_strength: float = 0.2, offset_strength: float = 0.0,
+                      generator=None) -> torch.Tensor:
+    """Random ``zoom @ rotation @ translation`` 4x4 of the input / reconstruction augmentation (reference ``:6-23``).
+
+    Host RNG, as in the reference.  The draws are issued in the reference's order and shapes - ``rand(1)`` (zoom),
+    ``randn(2)`` (plane normal), ``randn(2)`` (in-plane axis), ``randn(3)`` (offset, drawn even when its strength is 0) - so
+    with ``generator=None`` (the global torch RNG, which is what the reference uses) a run seeded with ``torch.manual_seed``
+    reproduces the reference's augmentation stream bit for bit (``tests/test_oracle_vs_reference.py``)."""
+    g = generator
+    zoom = torch.rand(1, generator=g) * zoom_strength - zoom_strength / 2 + 1.0
+    normal = torch.cat([rotation_strength * torch.randn(2, generator=g), torch.ones(1)])
+    normal = normal / normal.norm(2)
+    u = torch.cat([torch.ones(1), rotation_strength * torch.randn(2, generator=g)])
+    v = torch.linalg.cross(normal, u)
+    v = v / v.norm(2)
+    u = torch.linalg.cross(v, normal)
+    rot = torch.eye(4)
+    rot[:3, :3] = torch.stack([u, v, normal])
+    scale = torch.diag(torch.cat([zoom, zoom, zoom, torch.ones(1)]))
+    shift = torch.eye(4)
+    shift[:3, 3] = offset_strength * torch.randn(3, generator=g)
+    return scale @ rot @ shift
+
+
 def compute_rotation_matrix_from_ortho6d(ortho: torch.Tensor) -> torch.Tensor:
     """R6 -> homogeneous 4x4 rotation (Gram-Schmidt, columns x,y,z); ``[B,6] -> [B,4,4]``, differentiable."""
     return AF.r6_to_matrix(ortho)

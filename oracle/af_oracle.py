@@ -357,6 +357,33 @@ def random_aug_affine(gen: torch.Generator, rotation_strength=0.2, zoom_strength
     return z @ r @ t
 
 
+def get_random_affine(rotation_strength=0.2, zoom_strength=0.2, offset_strength=0.0):
+    """utils/transform_utils.py:6-23 on the GLOBAL torch RNG with the reference's exact draw sequence (``rand(1)``,
+    ``randn(2)``, ``randn(2)``, ``randn(3)`` - the last one also when ``offset_strength`` is 0): seeded identically, this
+    reproduces the reference's augmentation affines bit for bit."""
+    rz = torch.rand(1) * zoom_strength - zoom_strength / 2 + 1.0
+    n = torch.tensor((rotation_strength * torch.randn(2)).tolist() + [1.0])
+    n = n / n.norm(2)
+    one = torch.tensor([1.0] + (rotation_strength * torch.randn(2)).tolist())
+    two = torch.linalg.cross(n, one)
+    two = two / two.norm(2)
+    one = torch.linalg.cross(two, n)
+    r = torch.eye(4)
+    r[:3, :3] = torch.stack([one, two, n])
+    z = torch.diag(torch.tensor([rz.item(), rz.item(), rz.item(), 1.0]))
+    t = torch.eye(4)
+    t[:3, 3] = offset_strength * torch.randn(3)
+    return z @ r @ t
+
+
+def apply_affine_augmentation(affine_list, zoom_strength=0.1, offset_strength=0.1, rotation_strength=0.1):
+    """run_dl.py:208-223: one random affine per batch element, right-multiplied onto every affine of the list."""
+    B = affine_list[0].shape[0]
+    b_affine = torch.stack([get_random_affine(rotation_strength=rotation_strength, zoom_strength=zoom_strength,
+                                              offset_strength=offset_strength) for _ in range(B)])
+    return [a @ b_affine.to(a) for a in affine_list]
+
+
 # ----------------------------------------------------------------------------
 # a12  slice -> 3-D embedding                           models/hybrid_unet.py:71-94
 # ----------------------------------------------------------------------------
@@ -419,12 +446,14 @@ def skip_connector_sparse(x, b_grid_affines, n_views):
 # ----------------------------------------------------------------------------
 def reconstruction_model_input(b_label, b_image, nifti_affine, base_affine, view_affines, mlp_outs, init, hires_fov_mm,
                                hires_fov_vox, slice_fov_mm, slice_fov_vox, num_classes, offset_clip, zoom_clip, spat,
-                               aug_affine=None):
+                               aug_affine=None, augment_input=False, augment_recon=False, sample_augment_strength=1.0):
     """Restatement of ``get_reconstruction_model_input`` for ``label_slice_type='from-gt'``, ``opt-all``, all views active:
     hires resample of label (nearest) and image (bilinear) with ``base_affine`` (:251-259; the image call receives the
-    UPDATED nifti affine, as in the reference), one-hot (:261-264), ``Gpre = base^-1 @ view`` (:227-234) optionally times
-    an augmentation affine (:273-278), per-view ATM tail (:283-312), ``cat`` (:325).  ``mlp_outs[v]`` stands in for the
-    LocalizationNet output of view v."""
+    UPDATED nifti affine, as in the reference), one-hot (:261-264), ``Gpre = base^-1 @ view`` (:227-234), the input
+    augmentation (:273-278: ONE draw per batch element shared by all views, global RNG) or a given ``aug_affine``, per-view
+    ATM tail (:283-312) with the up-sampling of low-resolution slices (:193-197) and the per-view reconstruction
+    augmentation of the returned affine (:303-309), ``cat`` (:325).  ``mlp_outs[v]`` stands in for the LocalizationNet
+    output of view v.  Pinned against the reference's own function: golden ``model_input_s32*.npz``."""
     with torch.no_grad():
         lab, _, nii = nifti_grid_sample(b_label.unsqueeze(1), nifti_affine, target_fov_mm=hires_fov_mm, target_fov_vox=hires_fov_vox,
                                         is_label=True, pre_grid_sample_affine=base_affine)
@@ -433,13 +462,22 @@ def reconstruction_model_input(b_label, b_image, nifti_affine, base_affine, view
         lab = lab.squeeze(1)
     label = F.one_hot(lab, num_classes).permute(0, 4, 1, 2, 3)
     soft = label.float()
+    gpres = [input_affine_for_view(base_affine, va).to(nii) for va in view_affines]
+    if aug_affine is not None:
+        gpres = [g @ aug_affine.to(g) for g in gpres]
+    if augment_input:
+        gpres = apply_affine_augmentation(gpres, rotation_strength=0.1 * sample_augment_strength,
+                                          zoom_strength=0.2 * sample_augment_strength, offset_strength=0.0)
     slices, affines = [], []
-    for v, va in enumerate(view_affines):
-        gpre = input_affine_for_view(base_affine, va).to(nii)
-        if aug_affine is not None:
-            gpre = gpre @ aug_affine.to(gpre)
+    for v, gpre in enumerate(gpres):
         theta = view_theta(mlp_outs[v], init[v:v + 1, :6], init[v, 6:9], init[v:v + 1, 9:], offset_clip, zoom_clip, spat)
         ys, yl, yi, ga, _ = atm_tail_forward(soft, label, img, nii, gpre.float(), theta, slice_fov_mm, slice_fov_vox)
+        if [int(v_) for v_ in slice_fov_vox.tolist()] != [int(v_) for v_ in hires_fov_vox.tolist()]:       # :193-197
+            tgt = [int(v_) for v_ in hires_fov_vox.tolist()[:2]] + [1]
+            ys = F.interpolate(ys, size=tgt, mode="trilinear", align_corners=False)
+        if augment_recon:                                                                                # :303-309
+            ga = apply_affine_augmentation([ga], rotation_strength=0.1 * sample_augment_strength,
+                                           zoom_strength=0.2 * sample_augment_strength, offset_strength=0.0)[0].to(nii)
         slices.append(ys)
         affines.append(ga)
     return torch.cat(slices, dim=1).squeeze(-1), label, affines

@@ -115,3 +115,26 @@ def embed_case(S: int, c: int, V: int, B: int, seed: int):
         aug = torch.stack([synthetic.random_aug_affine(gen, 0.3, 0.3, 0.05) for _ in range(B)])
         gas.append(views[names[v % len(names)]][None].repeat(B, 1, 1) @ aug)
     return dict(S=S, c=c, V=V, B=B, x=x, affines=gas)
+
+
+def model_input_setup(S=32, slice_vox=None, aug=True):
+    """Inputs of the a11 goldens (shared with tests/): config (the reference's config_dict.json names), batch, MLP-head
+    outputs.  ``slice_vox`` < S exercises the low-resolution-slice up-sampling of run_dl.py:193-197."""
+    B, V, C = 2, 3, 8
+    names = ["p2CH", "p4CH", "4CH"]
+    sv = S if slice_vox is None else slice_vox
+    case = atm_case(sv, B, V, seed=91)            # params sized for the SLICE module: R = round(0.2 * prescan S)
+    case_vol = atm_case(S, B, V, seed=91)
+    views = synthetic.phantom_view_affines()
+    gen = torch.Generator().manual_seed(5)
+    base = torch.stack([synthetic.random_aug_affine(gen, 0.2, 0.1, 0.02) for _ in range(B)])
+    cfg = dict(clinical_view_affine_type="from-gt", label_slice_type="from-gt", hires_fov_mm=[192.0] * 3, hires_fov_vox=[S] * 3,
+               prescan_fov_mm=[192.0] * 3, prescan_fov_vox=[S] * 3, slice_fov_mm=[192.0, 192.0, 192.0 / sv], slice_fov_vox=[sv, sv, 1],
+               use_affine_theta=True, do_augment_input_orientation=aug, do_augment_recon_orientation=aug, aug_phases=["train"],
+               sample_augment_strength=1.0, view_optimization_mode="opt-all", base_views=names, offset_clip_value=0.2,
+               zoom_clip_value=0.0, affine_theta_optim_method="R6-vector", rotate_slice_to_min_principle=False)
+    batch = {"label": case_vol["lab"], "image": case_vol["image"][:, 0],
+             "additional_data": {"nifti_affine": case_vol["nii"],
+                                 "gt_view_affines": {**{n: views[n][None].repeat(B, 1, 1) for n in names}, "centroids": base}}}
+    params = [p.clone() for p in case_vol["params"]]     # [B, 6 + 3R + 1] with R = round(0.2 * S) (prescan size)
+    return cfg, batch, params, (B, V, C, names)

@@ -230,13 +230,45 @@ def gold_embed(R):
                             out=_np(out).astype(np.float32), dx=_np(x.grad), d_affines=np.stack([_np(g.grad) for g in gas]))
 
 
+def gold_model_input(R):
+    """a11 + a6: the reference's own ``get_reconstruction_model_input`` (running/run_dl.py:238-329, which calls
+    ``get_transformed`` :146-204, ``get_input_affine_for_atm`` :227-234 and ``apply_affine_augmentation`` :208-223 on the
+    GLOBAL torch RNG) executed unmodified via ``oracle.ref_import.load_run_dl``; LocalizationNets replaced by stubs that
+    return fixed MLP-head outputs.  ``torch.manual_seed(123)`` right before the call pins the augmentation stream."""
+    from oracle import cases
+    from oracle.ref_import import load_run_dl
+    RD = load_run_dl()
+    for tag, kw in (("model_input_s32", dict(S=32)), ("model_input_s32_lowres", dict(S=32, slice_vox=16)),
+                    ("model_input_s32_noaug", dict(S=32, aug=False))):
+        cfg, batch, params, (B, V, C, names) = cases.model_input_setup(**kw)
+        config = RD.DotDict(cfg)
+        container = R.learnable_transform.ATModulesContainer(config, C)
+        plist = []
+        for v, atm in enumerate(container):
+            p = params[v].clone().requires_grad_(True)
+            atm.localization_net = _Stub(p)
+            # _Stub holds a plain tensor: give the module a parameter so that the view counts as active (:399-405)
+            atm.localization_net.flag = torch.nn.Parameter(torch.zeros(1))
+            plist.append(p)
+        torch.manual_seed(123)
+        b_input, b_target, grid_affines = RD.get_reconstruction_model_input(batch, "train", config, C, container, None)
+        go = cases.pattern(b_input.shape, 1.0)
+        loss = (b_input * go).sum()
+        for v, g in enumerate(grid_affines):
+            loss = loss + (g * cases.pattern(g.shape, 2.0 + v)).sum()
+        loss.backward()
+        out = {"b_input": _np(b_input).astype(np.float32), "b_target_argmax": _np(b_target.argmax(1)).astype(np.uint8),
+               "grid_affines": np.stack([_np(g) for g in grid_affines]), "dparams": np.stack([_np(p.grad) for p in plist])}
+        np.savez_compressed(os.path.join(GOLD, tag + ".npz"), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     R = load_reference()
     groups = {"views": write_view_affines, "r6": gold_r6, "slice_small": gold_slice_small, "slice_cfg1": gold_slice_cfg1,
               "atm": gold_atm, "embed": gold_embed, "rotation_params": gold_rotation_params, "atm_other": gold_atm_other_params,
-              "atm_rotate": gold_atm_rotate}
+              "atm_rotate": gold_atm_rotate, "model_input": gold_model_input}
     for name in (sys.argv[1:] or list(groups)):          # python -m oracle.make_golden [group ...]
         groups[name](R)
     for f in sorted(os.listdir(GOLD)):

@@ -95,3 +95,52 @@ def load_reference() -> SimpleNamespace:
         get_clinical_cardiac_view_affines=clinical_cardiac_views.get_clinical_cardiac_view_affines,
     )
     return _CACHE
+
+
+_RUN_DL = None
+
+
+def load_run_dl():
+    """Import the reference's per-batch caller module ``running/run_dl.py`` (``get_reconstruction_model_input`` :238-329,
+    ``get_transformed`` :146-204, ``apply_affine_augmentation`` :208-223, ``get_input_affine_for_atm`` :227-234) unmodified.
+
+    Its module-level imports pull in packages that are absent here and irrelevant to those four functions; they are
+    replaced by empty ``sys.modules`` stubs: ``wandb``, ``dill``, ``monai`` (logging / metrics), ``pytorch_run_on_
+    recommended_gpu`` (GPU picker, ``run_dl.py:10-11``) and the reference's own ``utils/nnunetv2_utils`` (needs nnunetv2;
+    only ``DC_and_CE_loss`` is imported from it, for the loss)."""
+    global _RUN_DL
+    if _RUN_DL is not None:
+        return _RUN_DL
+    load_reference()
+
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+        return m
+
+    for name in ("wandb", "dill", "monai"):
+        try:
+            __import__(name)
+        except Exception:
+            stub(name)
+    try:
+        import pytorch_run_on_recommended_gpu.run_on_recommended_gpu  # noqa: F401
+    except Exception:
+        pkg = stub("pytorch_run_on_recommended_gpu")
+        pkg.run_on_recommended_gpu = stub("pytorch_run_on_recommended_gpu.run_on_recommended_gpu",
+                                          get_cuda_environ_vars=lambda *a, **k: {})
+    if "acquisition_focus.utils.nnunetv2_utils" not in sys.modules:
+        try:
+            import acquisition_focus.utils.nnunetv2_utils  # noqa: F401
+        except Exception:
+            stub("acquisition_focus.utils.nnunetv2_utils", DC_and_CE_loss=object)
+    from acquisition_focus.running import run_dl
+    from acquisition_focus.utils.python_utils import DotDict
+    _RUN_DL = SimpleNamespace(module=run_dl, DotDict=DotDict,
+                              get_reconstruction_model_input=run_dl.get_reconstruction_model_input,
+                              get_transformed=run_dl.get_transformed,
+                              apply_affine_augmentation=run_dl.apply_affine_augmentation,
+                              get_input_affine_for_atm=run_dl.get_input_affine_for_atm)
+    return _RUN_DL

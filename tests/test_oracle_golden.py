@@ -165,3 +165,33 @@ def test_atm_rotate_slice_to_min_principle(golden_dir):
         ((ys * cases.pattern(ys.shape, 1.0 + v)).sum() + (ga * cases.pattern(ga.shape, 2.0 + v)).sum()).backward()
         assert _close(params.grad.numpy(), g[f"dparams{v}"])
         assert _close(soft.grad.sum(-1).numpy(), g[f"dsoft_sum_w{v}"])
+
+
+MODEL_INPUT_CASES = [("model_input_s32", dict(S=32)), ("model_input_s32_lowres", dict(S=32, slice_vox=16)),
+                     ("model_input_s32_noaug", dict(S=32, aug=False))]
+
+
+@pytest.mark.parametrize("tag,kw", MODEL_INPUT_CASES)
+def test_reconstruction_model_input(golden_dir, tag, kw):
+    """a11 / a6: the restatement of running/run_dl.py:208-329 against outputs of the reference's OWN
+    get_reconstruction_model_input (executed unmodified by oracle/make_golden.py::gold_model_input), including the
+    augmentation affines drawn from the global torch RNG (seed 123) and the up-sampling of low-resolution slices."""
+    g = np.load(os.path.join(golden_dir, tag + ".npz"))
+    cfg, batch, params, (B, V, C, names) = cases.model_input_setup(**kw)
+    mlp = [p.clone().requires_grad_(True) for p in params]
+    init = torch.tensor([[1e-2, 0, 0, 0, 1e-2, 0, 0, 0, 0, 1.0]]).repeat(V, 1)
+    ad = batch["additional_data"]
+    torch.manual_seed(123)
+    b_in, b_t, affs = O.reconstruction_model_input(
+        batch["label"], batch["image"], ad["nifti_affine"], ad["gt_view_affines"]["centroids"].to(ad["nifti_affine"]),
+        [ad["gt_view_affines"][n] for n in names], mlp, init, torch.tensor(cfg["hires_fov_mm"]), torch.tensor(cfg["hires_fov_vox"]),
+        torch.tensor(cfg["slice_fov_mm"]), torch.tensor(cfg["slice_fov_vox"]), C, cfg["offset_clip_value"], cfg["zoom_clip_value"],
+        cfg["prescan_fov_vox"][0], augment_input=cfg["do_augment_input_orientation"], augment_recon=cfg["do_augment_recon_orientation"])
+    loss = (b_in * cases.pattern(b_in.shape, 1.0)).sum()
+    for v, a in enumerate(affs):
+        loss = loss + (a * cases.pattern(a.shape, 2.0 + v)).sum()
+    loss.backward()
+    assert np.array_equal(b_in.detach().numpy(), g["b_input"])
+    assert np.array_equal(b_t.argmax(1).numpy().astype(np.uint8), g["b_target_argmax"])
+    assert np.array_equal(torch.stack(affs).detach().numpy(), g["grid_affines"])
+    assert _close(torch.stack([m.grad for m in mlp]).numpy(), g["dparams"])
