@@ -43,6 +43,10 @@ def _is_dense(t: torch.Tensor) -> bool:
     return True
 
 
+def _layout_sig(t: torch.Tensor):
+    return (t.data_ptr(), t.numel(), tuple(t.stride()), t.dtype)
+
+
 def _zeros_like_strided(t: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
     out = torch.empty_strided(t.shape, t.stride(), dtype=dtype, device=t.device)
     return out.zero_()
@@ -72,6 +76,7 @@ def volume_min(volume: torch.Tensor, with_mask: bool = False) -> torch.Tensor:
                 L.check(lib.afb_volume_min_mask_half(L.ptr(volume), L.DTYPES[volume.dtype], volume.numel(), L.ptr(out), L.ptr(mask),
                                                      L.ptr(ws), L.stream_ptr(dev)), "afb_volume_min_mask_half")
             out._afb_mask = mask
+            out._afb_mask_sig = _layout_sig(volume)     # the record's bit order follows THIS memory layout and dtype
         else:
             L.check(lib.afb_volume_min(L.ptr(volume), L.DTYPES[volume.dtype], volume.numel(), L.ptr(out), L.ptr(ws),
                                        L.stream_ptr(dev)), "afb_volume_min")
@@ -221,6 +226,13 @@ class _SliceFn(torch.autograd.Function):
         ctx.pad_mode, ctx.pad_value = pad_mode, pad_value
         ctx.save_for_backward(volume.detach(), pad_dev if pad_dev is not None else torch.empty(0))
         ctx.pad_mask = getattr(pad_dev, "_afb_mask", None) if pad_dev is not None else None
+        sig = getattr(pad_dev, "_afb_mask_sig", None) if pad_dev is not None else None
+        if ctx.pad_mask is not None and sig is not None and sig != _layout_sig(volume):
+            ctx.pad_mask = None      # record built for another tensor / layout / dtype: MinBackward re-reads the volume instead
+        if ctx.pad_mask is not None and volume.dtype == torch.float32 and ctx.pad_mask.numel() != int(L.lib().afb_min_mask_bytes(volume.numel())):
+            ctx.pad_mask = None
+        # sharded batches (parallel.global_pad): d(out)/d(pad) must be summed over the ranks before it is spread over the minima
+        ctx.dpad_reduce = getattr(pad_dev, "_afb_dpad_reduce", None) if pad_dev is not None else None
         ctx.in_dtype = view_input.dtype
         ga = ga.clone()          # each Function call owns its differentiable output
         nii = nii if nii is not None else torch.empty(0, device=volume.device)
@@ -281,6 +293,8 @@ class _SliceFn(torch.autograd.Function):
                     d_pad = torch.zeros(1, dtype=torch.float32, device=dev)
                     L.check(lib.afb_slice_pad_grad(C.byref(vd), C.byref(vs), Do, Ho, Wo, L.ptr(go), L.ptr(d_pad), st),
                             "afb_slice_pad_grad")
+                    if ctx.dpad_reduce is not None:
+                        ctx.dpad_reduce(d_pad)
                     d_vol = torch.empty_strided(volume.shape, volume.stride(), dtype=torch.float32, device=dev)
                     if ctx.pad_mask is not None:        # 1-bit record left by the forward's min pass: no volume re-read
                         fill = lib.afb_min_grad_fill_mask if volume.dtype == torch.float32 else lib.afb_min_grad_fill_mask_half
@@ -379,7 +393,8 @@ def _side_stream(dev) -> "torch.cuda.Stream":
 
 
 def acquire_views(x_soft_label, x_label, x_image, nifti_affine, gpre, params, init, *, offset_clip, zoom_clip,
-                  spat, slice_fov_mm, slice_fov_vox, soft_pad="global_min", image_pad="global_min", overlap_streams=None):
+                  spat, slice_fov_mm, slice_fov_vox, soft_pad="global_min", image_pad="global_min", overlap_streams=None,
+                  pad_exchange=None):
     """Fused tail of ``AffineTransformModule.forward`` for all views at once.
 
     x_soft_label ``[B,C,D,H,W]`` float (grad flows), x_label ``[B,C,D,H,W]`` int (nearest, no grad) or None,
@@ -387,7 +402,10 @@ def acquire_views(x_soft_label, x_label, x_image, nifti_affine, gpre, params, in
     (R6 | offset logits | zoom logit: the MLP-head output), init ``[V,10]`` fp32.
     Returns ``(y_soft[B,V,C,Do,Ho,Wo], y_label, y_image, grid_affine[B,V,4,4], nii_affine[B,V,4,4], theta[B,V,4,4])``.
     Views are concatenated batch-major, i.e. ``y_soft.flatten(1,2).squeeze(-1)`` is the ``[B, V*C, H, W]`` encoder
-    input the reference builds with ``torch.cat(slices, dim=1)`` (running/run_dl.py:325)."""
+    input the reference builds with ``torch.cat(slices, dim=1)`` (running/run_dl.py:325).
+    ``pad_exchange`` (sharded batches, ``parallel.exchange_pads``): maps the local ``[min, multiplicity]`` pads of
+    (soft label, image) to those of the whole batch, so that every rank pads with the reference's whole-batch
+    ``volume.min()`` (utils/nifti_utils.py:200)."""
     L.require_cuda(x_soft_label, "x_soft_label")
     dev = x_soft_label.device
     if overlap_streams is None:
@@ -412,14 +430,36 @@ def acquire_views(x_soft_label, x_label, x_image, nifti_affine, gpre, params, in
                 yi = _run_slice(x_image, p.detach(), spec, slice_fov_vox, L.BILINEAR, image_pad, prepared)[0]
         return yl, yi
 
-    if overlap_streams and not isinstance(soft_pad, torch.Tensor):
+    has_l = x_label is not None and x_label.numel() > 0
+    has_i = x_image is not None and x_image.numel() > 0
+    if pad_exchange is not None and soft_pad == "global_min" and (not has_i or image_pad == "global_min"):
+        # sharded batch: label slicing (needs no pad) on the side stream UNDER the local min passes; then ONE small exchange
+        # turns the local pads into whole-batch pads; soft and image slicings follow on the caller's stream
+        main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+        Do, Ho, Wo = (int(v) for v in slice_fov_vox)
+        xs = x_soft_label if _is_dense(x_soft_label) else x_soft_label.contiguous()
+        xl = (x_label if _is_dense(x_label) else x_label.contiguous()) if has_l else None
+        xi = (x_image.detach() if _is_dense(x_image) else x_image.detach().contiguous()) if has_i else None
+        y_label = torch.empty((B, V, xl.shape[1], Do, Ho, Wo), dtype=xl.dtype, device=dev) if has_l else None
+        forked = main.record_event()
+        if has_l:
+            side.wait_event(forked)
+            with torch.cuda.stream(side):
+                _slice_forward_raw(xl, prepared[0], slice_fov_vox, L.NEAREST, L.PAD_ZERO, 0.0, None, out=y_label)
+        want_dvol = xs.requires_grad and torch.is_grad_enabled()
+        local = [volume_min(xs.detach(), with_mask=want_dvol)] + ([volume_min(xi)] if has_i else [])
+        pads = pad_exchange(local)
+        y_soft, ga, nii, theta = _run_slice(xs, p, spec, slice_fov_vox, L.BILINEAR, pads[0], prepared)
+        y_image = None
+        if has_i:
+            y_image = _slice_forward_raw(xi, prepared[0], slice_fov_vox, L.BILINEAR, L.PAD_DEVICE, 0.0, pads[1])
+        main.wait_stream(side)
+    elif overlap_streams and not isinstance(soft_pad, torch.Tensor):
         # the label / image slicings (gather kernels, latency bound) run on a side stream UNDER the soft volume's min pass
         # (HBM bound), then the soft slicing follows on the caller's stream.  Their outputs are allocated on the caller's
         # stream and the side stream is joined before returning, so the caching allocator needs no cross-stream bookkeeping.
         main, side = torch.cuda.current_stream(dev), _side_stream(dev)
         Do, Ho, Wo = (int(v) for v in slice_fov_vox)
-        has_l = x_label is not None and x_label.numel() > 0
-        has_i = x_image is not None and x_image.numel() > 0
         xl = (x_label if _is_dense(x_label) else x_label.contiguous()) if has_l else None
         xi = (x_image.detach() if _is_dense(x_image) else x_image.detach().contiguous()) if has_i else None
         y_label = torch.empty((B, V, xl.shape[1], Do, Ho, Wo), dtype=xl.dtype, device=dev) if has_l else None

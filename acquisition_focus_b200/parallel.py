@@ -43,13 +43,44 @@ def reduce_view_grads(d_params: torch.Tensor, group=None) -> torch.Tensor:
 
 
 def allreduce_pad(min_count: torch.Tensor, group=None) -> torch.Tensor:
-    """Combine per-shard ``[min, multiplicity]`` into the global one (keeps the reference's whole-batch
-    ``volume.min()`` semantics under sharding).  Two tiny collectives (min, then sum of the multiplicities
-    of the ranks that hold the global minimum)."""
+    """Combine per-shard ``[min, multiplicity]`` (or a stack ``[k, 2]`` of them) into the global one (keeps the reference's
+    whole-batch ``volume.min()`` semantics under sharding).  ONE tiny collective: every rank gathers all pairs and takes the
+    minimum and the summed multiplicity of the ranks that hold it (no host synchronisation)."""
     if not is_distributed():
         return min_count
-    m = min_count[:1].clone()
-    dist.all_reduce(m, op=dist.ReduceOp.MIN, group=group)
-    cnt = torch.where(min_count[:1] == m, min_count[1:2], torch.zeros_like(min_count[1:2]))
-    dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
-    return torch.cat([m, cnt])
+    world = dist.get_world_size(group)
+    flat = min_count.reshape(-1).contiguous()
+    buf = torch.empty(world * flat.numel(), dtype=flat.dtype, device=flat.device)
+    dist.all_gather_into_tensor(buf, flat, group=group)
+    pairs = buf.view(world, -1, 2)
+    m = pairs[..., 0].min(dim=0).values
+    cnt = torch.where(pairs[..., 0] == m, pairs[..., 1], torch.zeros_like(pairs[..., 1])).sum(dim=0)
+    return torch.stack([m, cnt], dim=-1).view(min_count.shape)
+
+
+def exchange_pads(local, group=None):
+    """Per-shard pads (``functional.volume_min`` results, MinBackward records attached) -> whole-batch pads: ONE all-gather
+    for all of them, the records carried over, and a hook that sums ``d(out)/d(pad)`` over the ranks in the backward pass
+    before it is spread over the global minima.  Identity when not distributed.  Pass it as ``pad_exchange`` of
+    :func:`functional.acquire_views` (which keeps the label slicing overlapped under the min pass)."""
+    if not is_distributed():
+        return list(local)
+    glob = allreduce_pad(torch.stack(list(local)), group)
+    out = []
+    for i, loc in enumerate(local):
+        g = glob[i].contiguous()
+        for attr in ("_afb_mask", "_afb_mask_sig"):
+            if hasattr(loc, attr):
+                setattr(g, attr, getattr(loc, attr))
+        g._afb_dpad_reduce = lambda d_pad, _grp=group: dist.all_reduce(d_pad, op=dist.ReduceOp.SUM, group=_grp)
+        out.append(g)
+    return out
+
+
+def global_pads(volumes, with_mask, group=None):
+    """``[min, multiplicity]`` of each tensor of ``volumes`` over the WHOLE sharded batch, ready to be passed as ``soft_pad`` /
+    ``image_pad`` of :func:`functional.acquire_views`: one local min pass per tensor (``with_mask[i]``: also leave the 1-bit
+    MinBackward record) + :func:`exchange_pads`.  With these pads a sharded run returns exactly what the unsharded call
+    returns (``tests/test_gpu_multirank.py``)."""
+    from . import functional as AF
+    return exchange_pads([AF.volume_min(v, with_mask=m) for v, m in zip(volumes, with_mask)], group)

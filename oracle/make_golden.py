@@ -181,6 +181,12 @@ def gold_atm(R):
                     f"yi{v}": _np(r["yi"]), f"ga{v}": _np(r["ga"]), f"na{v}": _np(r["na"]),
                     f"dparams{v}": _np(r["dparams"]),
                     f"ys_ch3_{v}": _np(r["ys"][:, 3]).astype(np.float32)})
+    # dVolume at the headline shape: projections of the gradient summed over the three views (what one fused acquisition
+    # accumulates into soft.grad), plus its value at a fixed pseudo-random set of voxels
+    dsoft = sum(r["dsoft"] for r in res)
+    pick = np.random.default_rng(7).integers(0, dsoft.numel(), size=4096)
+    out.update({"dsoft_sum_w": _np(dsoft.sum(-1)), "dsoft_sum_d": _np(dsoft.sum(2)), "dsoft_pick_idx": pick,
+                "dsoft_pick": _np(dsoft).reshape(-1)[pick], "dsoft_absmax": np.float32(dsoft.abs().max().item())})
     np.savez_compressed(os.path.join(GOLD, "atm_s128.npz"), **out)
 
 

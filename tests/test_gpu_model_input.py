@@ -114,3 +114,38 @@ def test_reconstruction_model_input_matches_oracle():
     for v in range(V):
         g, r = container[v].localization_net.p.grad.cpu(), mlp[v].grad
         assert (g - r).abs().max().item() <= 1e-4 * r.abs().max().item()
+
+
+@pytest.mark.parametrize("tag,kw", [("model_input_s32", dict(S=32)), ("model_input_s32_lowres", dict(S=32, slice_vox=16)),
+                                    ("model_input_s32_noaug", dict(S=32, aug=False))])
+def test_reconstruction_model_input_golden(golden_dir, tag, kw):
+    """a11 / a6 against the reference ITSELF: goldens minted by executing running/run_dl.py:238-329 unmodified
+    (oracle/make_golden.py::gold_model_input), with input AND reconstruction augmentation drawn from the global torch RNG
+    (seed 123: the product issues the reference's draw sequence, so the augmentation affines are bitwise the same) and, in
+    the `lowres` case, 16x16 slices up-sampled to the 32^3 hires FOV (run_dl.py:193-197)."""
+    import os
+    import numpy as np
+    import acquisition_focus_b200 as afb
+    from acquisition_focus_b200.running.model_input import get_reconstruction_model_input
+    g = np.load(os.path.join(golden_dir, tag + ".npz"))
+    cfgd, batch, params, (B_, V_, C_, names) = cases.model_input_setup(**kw)
+    cfg = types.SimpleNamespace(**cfgd)
+    nets = iter([_Stub(params[v].clone()) for v in range(V_)])
+    container = afb.ATModulesContainer(cfg, C_, localization_net_factory=lambda: next(nets)).cuda()
+    ad = batch["additional_data"]
+    cb = {"label": batch["label"].cuda(), "image": batch["image"].cuda(),
+          "additional_data": {"nifti_affine": ad["nifti_affine"].cuda(), "gt_view_affines": {k: v.cuda() for k, v in ad["gt_view_affines"].items()}}}
+    torch.manual_seed(123)
+    b_input, b_target, grid_affines = get_reconstruction_model_input(cb, "train", cfg, C_, container)
+    loss = (b_input * cases.pattern(b_input.shape, 1.0).cuda()).sum()
+    for v, a in enumerate(grid_affines):
+        loss = loss + (a * cases.pattern(a.shape, 2.0 + v).cuda()).sum()
+    loss.backward()
+    assert np.array_equal(b_target.argmax(1).cpu().numpy().astype(np.uint8), g["b_target_argmax"])      # hires nearest: bit-exact
+    ga = torch.stack([a.detach().cpu() for a in grid_affines]).numpy()
+    e_ga = np.abs(ga - g["grid_affines"]).max() / np.abs(g["grid_affines"]).max()
+    e_in = np.abs(b_input.detach().cpu().numpy() - g["b_input"]).max()
+    dp = torch.stack([container[v].localization_net.p.grad.cpu() for v in range(V_)]).numpy()
+    e_dp = np.abs(dp - g["dparams"]).max() / np.abs(g["dparams"]).max()
+    print(f"{tag}: grid_affine {e_ga:.2e}  b_input {e_in:.2e}  dparams {e_dp:.2e}")
+    assert e_ga <= 2e-6 and e_in <= 2e-5 and e_dp <= 1e-4, (e_ga, e_in, e_dp)

@@ -23,6 +23,9 @@ def _worker(rank, world, port, q):
         mc = torch.tensor([mine.min().item(), float((mine == mine.min()).sum())])
         tot = par.allreduce_pad(mc)
         ok_p = tot[0].item() == 1.0 and tot[1].item() == 4.0
+        # several tensors at once ([k,2] stack, one collective): second pair has its minimum on rank 1 only
+        both = par.allreduce_pad(torch.stack([mc, torch.tensor([5.0 - 3.0 * rank, 2.0 + rank])]))
+        ok_p = ok_p and both.tolist() == [[1.0, 4.0], [2.0, 3.0]]
         q.put((rank, lo, hi, ok_g, ok_p))
     finally:
         dist.destroy_process_group()
