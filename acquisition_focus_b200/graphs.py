@@ -10,7 +10,8 @@ with a single launch.
     static_input.copy_(new_values); outs = step()              # replay; outputs are static tensors
 
 Inputs must be static tensors (update them in place); tensors created inside the step live in the graph's private
-memory pool.  The reference has no counterpart (its path issues ~10^3 ATen launches per call).
+memory pool.  NCCL collectives issued through ``torch.distributed`` inside the step are captured with it (every rank must
+capture and replay the same sequence), which is how ``bench.py`` runs the sharded step at 8 volumes per GPU.  The reference has no counterpart (its path issues ~10^3 ATen launches per call).
 """
 from __future__ import annotations
 
@@ -30,7 +31,9 @@ class GraphedStep:
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # thread_local: other threads (the NCCL watchdog of a captured all-reduce, an NVML poller) may keep calling the CUDA
+        # runtime while this thread captures
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.outputs = fn()
 
     def __call__(self):

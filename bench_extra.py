@@ -155,6 +155,55 @@ def cfg3(afb, dev):
     return out
 
 
+def cfg3_summary(afb, dev, B=2, V=6):
+    """cfg3 for the driver-run bench line: all six U-Net stages at B=2, V=6, forward and forward+backward, per stage and summed,
+    with the HBM roofline fraction of each stage's forward (compulsory bytes: the [B,V*c,S^3] output written once + the feature
+    maps read once) and the same op through ATen's sm_100 kernels (oracle op sequence on the GPU), stage 0 and summed."""
+    from oracle import cases
+    import json as _json
+    peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm = float(_json.load(open(peaks))["hbm_gbs"]) if os.path.exists(peaks) else 6650.0
+    stages, tot = [], {"fwd_ms": 0.0, "fwd_bwd_ms": 0.0, "bytes_fwd": 0, "bytes_bwd": 0, "aten_fwd_ms": 0.0, "aten_fwd_bwd_ms": 0.0}
+    for c, S in ((16, 128), (32, 64), (64, 32), (128, 16), (256, 8), (256, 4)):
+        case = cases.embed_case(S, c, V, B, seed=300 + S)
+        x = case["x"].to(dev).requires_grad_(True)
+        gas = [a.to(dev).requires_grad_(True) for a in case["affines"]]
+        aff = torch.stack(gas, 0)
+        go = torch.randn(B, V * c, S, S, S, device=dev)
+        sc = afb.SkipConnector(V)
+        f, _ = timeit(lambda: afb.embed_slices(x.detach(), aff.detach(), V), reps=5, warm=2)
+
+        def fb():
+            x.grad = None
+            for a in gas:
+                a.grad = None
+            sc(x, gas).backward(go)
+        fbt, _ = timeit(fb, reps=5, warm=2)
+        from oracle import af_oracle as O
+
+        def rfb():
+            x.grad = None
+            for a in gas:
+                a.grad = None
+            O.skip_connector(x, gas, V).backward(go)
+        rf, _ = timeit(lambda: O.skip_connector(x.detach(), [a.detach() for a in gas], V), reps=1, warm=1)
+        rfbt, _ = timeit(rfb, reps=1, warm=1)
+        nb_f = B * V * c * S ** 3 * 4 + B * V * c * S * S * 4
+        nb_b = B * V * c * (int(2.5 * S * S) + 2 * S * S) * 4          # slab of grad_out read + x read + dX written
+        stages.append({"c": c, "S": S, "fwd_ms": f, "fwd_bwd_ms": fbt, "bytes_fwd": nb_f, "fwd_gbs": nb_f / f / 1e6,
+                       "fwd_frac_of_hbm": nb_f / f / 1e6 / hbm, "aten_cuda_fwd_ms": rf, "aten_cuda_fwd_bwd_ms": rfbt})
+        tot["fwd_ms"] += f; tot["fwd_bwd_ms"] += fbt; tot["bytes_fwd"] += nb_f; tot["bytes_bwd"] += nb_b
+        tot["aten_fwd_ms"] += rf; tot["aten_fwd_bwd_ms"] += rfbt
+        del x, gas, aff, go
+        torch.cuda.empty_cache()
+    tot["fwd_gbs"] = tot["bytes_fwd"] / tot["fwd_ms"] / 1e6
+    tot["fwd_frac_of_hbm"] = tot["fwd_gbs"] / hbm
+    tot["value"] = 1e3 / tot["fwd_bwd_ms"]
+    tot["unit"] = "embeddings/s (fwd+bwd, 6 stages, B=2, V=6)"
+    return {"config": f"cfg3: slice-to-3D embedding, V={V} views, B={B}, six stages (c,S) = (16,128) ... (256,4)", "stages": stages,
+            "all_stages": tot, "hbm_peak_gbs": hbm}
+
+
 def cfg5(afb, dev):
     out = []
     S, V, C = 256, 16, 8
