@@ -28,6 +28,16 @@ namespace afb {
 constexpr int ETHREADS = 256;
 constexpr int ECH = 16;             // channels per thread in the backward
 
+__device__ __forceinline__ AxisConst make_axis_dev(int K) {   // device twin of make_axis (same IEEE fp32 results)
+    AxisConst a;
+    a.K = K;
+    a.km1 = (float)(K - 1);
+    a.kf = (float)K;
+    a.step = K > 1 ? __fdiv_rn(2.0f, (float)(K - 1)) : 0.0f;
+    a.inv_k = (K & (K - 1)) == 0 ? __fdiv_rn(1.0f, (float)K) : 0.0f;
+    return a;
+}
+
 struct EmbedView {                // per (b, v), shared memory
     float t[12];                  // inverse(normalised affine)[:3,:] fp32 = affine_grid theta
     float fwd[12];                // normalised affine A[:3,:] (fp32 copy) for the backward's candidate boxes
@@ -340,6 +350,242 @@ embed_bwd_kernel(const float* __restrict__ go, const float* __restrict__ x, cons
     if (threadIdx.x == 0) embed_chain(ev, dT, d_aff + ((size_t)v * B + b) * 16);
 }
 
+
+// ================================================================================================
+// Batched, single-pass forward/backward over ALL stages of one U-Net pass (HybridUnet.forward embeds the six encoder skips
+// with the same affines, models/hybrid_unet.py:40-43).
+//
+// forward: ONE launch.  A CTA owns a chunk of consecutive output rows (d,h) of one (b,v) and ALL its c channels.  Phase 1
+// streams zeros over the chunk (16-byte stores, the ~97 % of the output that is zero); after a CTA barrier phase 2 patches
+// the slab voxels of the SAME rows (exact bit-level tap code).  The patch stores land microseconds after the zero stores of
+// the same sectors, i.e. while those lines are still dirty in L2, so every sector reaches HBM once - the earlier
+// zero-kernel-then-slab-kernel pair re-fetched each slab sector from HBM (1.6 GB of zeros had long been evicted).
+// The slab is found per row along w (the contiguous axis): ix is affine in w with slope t[0] (index units), so the row
+// meets |ix - S/2| < 1 in one interval; |t0| ~ 0 (slab parallel to the rows) degenerates to "whole row or nothing".
+// ================================================================================================
+constexpr int EMAX_STAGES = 8;
+
+struct EmbedStage {
+    const float* x;            // [B, V*c, S, S]
+    float* out;                // [B, V*c, S, S, S]              (forward)
+    const float* go;           // grad_out, same shape as out    (backward)
+    float* dx;                 // [B, V*c, S, S] | NULL          (backward)
+    int c, S;
+    int rows_per_cta;          // forward: rows (d,h) per CTA
+    unsigned chunks;           // forward: row chunks per (b,v);  backward: pixel tiles x channel chunks per (b,v)
+    unsigned cta_begin;        // first CTA of this stage in the flattened grid
+    int ch_chunks;             // backward: channel chunks
+};
+
+struct EmbedBatch {
+    int n, B, V;
+    EmbedStage st[EMAX_STAGES];
+};
+
+__device__ __forceinline__ int stage_of_cta(const EmbedBatch& eb, unsigned cta) {
+    int s = 0;
+#pragma unroll
+    for (int q = 1; q < EMAX_STAGES; ++q)
+        if (q < eb.n && cta >= eb.st[q].cta_begin) s = q;
+    return s;
+}
+
+__global__ void __launch_bounds__(ETHREADS)
+embed_fwd_fused_kernel(const __grid_constant__ EmbedBatch eb, const EmbedView* __restrict__ views) {
+    const int si = stage_of_cta(eb, blockIdx.x);
+    const EmbedStage& sg = eb.st[si];
+    const unsigned local = blockIdx.x - sg.cta_begin;
+    const int bv = (int)(local / sg.chunks), chunk = (int)(local - (unsigned)bv * sg.chunks);
+    const int S = sg.S, c = sg.c;
+    const int nrows = S * S;
+    const int r0 = chunk * sg.rows_per_cta, r1 = min(nrows, r0 + sg.rows_per_cta);
+    const size_t S2 = (size_t)S * S, S3 = S2 * S;
+    float* __restrict__ ob = sg.out + (size_t)bv * c * S3;           // [b, v*c .. v*c+c) == (b*V + v) * c channels
+    // ---- phase 1: zeros over rows [r0, r1) of every channel (contiguous span per channel) ----
+    const size_t span = (size_t)(r1 - r0) * S;                        // floats per channel
+    const size_t off0 = (size_t)r0 * S;
+    if ((S & 3) == 0 && (((uintptr_t)sg.out) & 15u) == 0) {
+        const int span4 = (int)(span >> 2);
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int ch = 0; ch < c; ++ch) {
+            float4* __restrict__ p = reinterpret_cast<float4*>(ob + (size_t)ch * S3 + off0);
+            for (int i = threadIdx.x; i < span4; i += ETHREADS) __stcs(p + i, z4);
+        }
+    } else {
+        for (int ch = 0; ch < c; ++ch) {
+            float* __restrict__ p = ob + (size_t)ch * S3 + off0;
+            for (int i = threadIdx.x; i < (int)span; i += ETHREADS) p[i] = 0.0f;
+        }
+    }
+    __syncthreads();              // orders the zero stores before the patch stores of the same addresses (CTA scope)
+    // ---- phase 2: patch the slab voxels of these rows ----
+    float t[12];
+#pragma unroll
+    for (int q = 0; q < 12; ++q) t[q] = __ldg(views[bv].t + q);
+    const AxisConst ax = make_axis_dev(S);
+    const float Sf = (float)S, mid = (float)(S >> 1);
+    const float a1 = 2.0f / Sf, a0 = 1.0f / Sf - 1.0f;              // closed-form base coordinate (2k+1)/S-1 for the row solve
+    const float t0 = t[0];                                           // d ix / d w in index units
+    const bool flat = fabsf(t0) * Sf < 0.05f;                        // ix changes by < 0.05 voxel along the whole row
+    const float* __restrict__ xs = sg.x + (size_t)bv * c * S2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int row = r0 + warp; row < r1; row += ETHREADS / 32) {
+        const int d = row / S, h = row - d * S;
+        const float g0 = t[0] * a0 + t[1] * (a1 * h + a0) + t[2] * (a1 * d + a0) + t[3];      // grid x at w = 0 (closed form)
+        const float ix0 = ((g0 + 1.0f) * Sf - 1.0f) * 0.5f;
+        int lo, hi;                                                   // candidate interval [lo, hi] along w
+        if (flat) {
+            if (fabsf(ix0 + 0.5f * t0 * Sf - mid) < 1.1f) { lo = 0; hi = S - 1; } else { lo = 1; hi = 0; }
+        } else {
+            const float wc = (mid - ix0) / t0, half = 1.05f / fabsf(t0);
+            lo = max(0, (int)ceilf(wc - half));
+            hi = min(S - 1, (int)floorf(wc + half));
+        }
+        const float by = base_coord(h, ax), bz = base_coord(d, ax);
+        for (int w = lo + lane; w <= hi; w += 32) {
+            const Tap tp = taps_of(t, base_coord(w, ax), by, bz, S);
+            if (tp.inb == 0u) continue;
+            float* __restrict__ o = ob + (size_t)row * S + w;
+#pragma unroll 4
+            for (int ch = 0; ch < c; ++ch) {
+                const float* __restrict__ xc = xs + (size_t)ch * S2;
+                float acc = 0.0f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if ((tp.inb >> q) & 1u) acc = __fadd_rn(acc, __fmul_rn(__ldg(xc + tp.off[q]), tp.w[q]));
+                o[(size_t)ch * S3] = acc;
+            }
+        }
+    }
+}
+
+// backward, all stages in one launch: the gather kernel above (embed_bwd_kernel's body) per (stage, pixel tile, channel chunk,
+// b*V + v); the 12 sums of d(theta) are accumulated over ALL stages (the chain through inverse() and the column normalisation
+// is linear in them) and chained once by the last CTA of each (b,v).
+__global__ void __launch_bounds__(ETHREADS)
+embed_bwd_fused_kernel(const __grid_constant__ EmbedBatch eb, const EmbedView* __restrict__ views, float* __restrict__ d_aff,
+                       double* __restrict__ ws_acc, unsigned* __restrict__ ws_counter, unsigned ctas_per_bv) {
+    __shared__ EmbedView ev;
+    __shared__ float base[256];
+    __shared__ float red[ETHREADS / 32][12];
+    __shared__ double dT[12];
+    __shared__ bool is_last;
+    const int si = stage_of_cta(eb, blockIdx.x);
+    const EmbedStage& sg = eb.st[si];
+    const unsigned local = blockIdx.x - sg.cta_begin;
+    const int bv = (int)(local / sg.chunks);
+    const unsigned rest = local - (unsigned)bv * sg.chunks;
+    const int tile = (int)(rest / (unsigned)sg.ch_chunks), cchunk = (int)(rest - (unsigned)tile * (unsigned)sg.ch_chunks);
+    const int S = sg.S, c = sg.c, B = eb.B, V = eb.V;
+    const int b = bv / V, v = bv % V;
+    {
+        const unsigned* __restrict__ src = reinterpret_cast<const unsigned*>(views + bv);
+        unsigned* dst = reinterpret_cast<unsigned*>(&ev);
+        for (int i = threadIdx.x; i < (int)(sizeof(EmbedView) / 4); i += ETHREADS) dst[i] = __ldg(src + i);
+    }
+    const AxisConst ax = make_axis_dev(S);
+    const bool use_tab = S <= 256;
+    if (use_tab) for (int i = threadIdx.x; i < S; i += ETHREADS) base[i] = base_coord(i, ax);
+    __syncthreads();
+    float part[12];
+#pragma unroll
+    for (int q = 0; q < 12; ++q) part[q] = 0.0f;
+    const int pix = tile * ETHREADS + threadIdx.x;
+    const int c0 = cchunk * ECH;
+    const int nch = min(ECH, c - c0);
+    const size_t S2 = (size_t)S * S, S3 = S2 * S;
+    if (pix < S * S) {
+        const int r = pix / S, q = pix % S;
+        const int mid = S >> 1;
+        const float Sf = (float)S;
+        const float pn[3] = {(2.0f * mid + 1.0f) / Sf - 1.0f, (2.0f * q + 1.0f) / Sf - 1.0f, (2.0f * r + 1.0f) / Sf - 1.0f};
+        int lo[3], hi[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float g = ev.fwd[k * 4 + 0] * pn[0] + ev.fwd[k * 4 + 1] * pn[1] + ev.fwd[k * 4 + 2] * pn[2] + ev.fwd[k * 4 + 3];
+            const float vc = ((g + 1.0f) * Sf - 1.0f) * 0.5f;
+            const float ext = fabsf(ev.fwd[k * 4 + 0]) + fabsf(ev.fwd[k * 4 + 1]) + fabsf(ev.fwd[k * 4 + 2]) + 0.05f;
+            lo[k] = max(0, (int)ceilf(vc - ext));
+            hi[k] = min(S - 1, (int)floorf(vc + ext));
+        }
+        const float* __restrict__ gbase = sg.go + ((size_t)bv * c + c0) * S3;
+        const float* __restrict__ xp = sg.x + ((size_t)bv * c + c0) * S2 + pix;
+        float acc[ECH], xv[ECH];
+#pragma unroll
+        for (int ch = 0; ch < ECH; ++ch) { acc[ch] = 0.0f; xv[ch] = (d_aff && ch < nch) ? __ldg(xp + (size_t)ch * S2) : 0.0f; }
+        for (int d = lo[2]; d <= hi[2]; ++d) {
+            const float bz = use_tab ? base[d] : base_coord(d, ax);
+            for (int h = lo[1]; h <= hi[1]; ++h) {
+                const float by = use_tab ? base[h] : base_coord(h, ax);
+                for (int w = lo[0]; w <= hi[0]; ++w) {
+                    const float bx = use_tab ? base[w] : base_coord(w, ax);
+                    const Tap tp = taps_of(ev.t, bx, by, bz, S);
+                    if (tp.inb == 0u) continue;
+                    int tt = -1;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (((tp.inb >> k) & 1u) && tp.off[k] == pix) tt = k;
+                    if (tt < 0) continue;
+                    const float wt = tp.w[tt];
+                    const float* __restrict__ gp = gbase + ((size_t)d * S + h) * S + w;
+                    float ssum = 0.0f;
+#pragma unroll
+                    for (int ch = 0; ch < ECH; ++ch) {
+                        if (ch < nch) {
+                            const float gv = __ldg(gp + (size_t)ch * S3);
+                            acc[ch] = fmaf(wt, gv, acc[ch]);
+                            ssum = fmaf(gv, xv[ch], ssum);
+                        }
+                    }
+                    if (d_aff) {
+                        const int dy = tt & 1, dz = tt >> 1;
+                        const float hs = 0.5f * Sf;
+                        const float ggx = tp.sx * ssum * tp.wy[dy] * tp.wz[dz] * hs;
+                        const float ggy = (dy ? ssum : -ssum) * tp.wx * tp.wz[dz] * hs;
+                        const float ggz = (dz ? ssum : -ssum) * tp.wx * tp.wy[dy] * hs;
+                        part[0] += ggx * bx; part[1] += ggx * by; part[2] += ggx * bz; part[3] += ggx;
+                        part[4] += ggy * bx; part[5] += ggy * by; part[6] += ggy * bz; part[7] += ggy;
+                        part[8] += ggz * bx; part[9] += ggz * by; part[10] += ggz * bz; part[11] += ggz;
+                    }
+                }
+            }
+        }
+        if (sg.dx) {
+            float* __restrict__ dxp = sg.dx + ((size_t)bv * c + c0) * S2 + pix;
+#pragma unroll
+            for (int ch = 0; ch < ECH; ++ch)
+                if (ch < nch) dxp[(size_t)ch * S2] = acc[ch];
+        }
+    }
+    if (!d_aff) return;
+    const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int q = 0; q < 12; ++q) {
+        const float rr = warp_sum(part[q]);
+        if (lane == 0) red[wi][q] = rr;
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        double tsum = 0.0;
+#pragma unroll
+        for (int ww = 0; ww < ETHREADS / 32; ++ww) tsum += (double)red[ww][threadIdx.x];
+        if (tsum != 0.0) atomicAdd(ws_acc + (size_t)bv * 16 + threadIdx.x, tsum);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(ws_counter + bv, 1u) == ctas_per_bv - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x < 12) {
+        dT[threadIdx.x] = __ldcg(ws_acc + (size_t)bv * 16 + threadIdx.x);
+        ws_acc[(size_t)bv * 16 + threadIdx.x] = 0.0;
+    }
+    if (threadIdx.x == 0) ws_counter[bv] = 0u;
+    __syncthreads();
+    if (threadIdx.x == 0) embed_chain(ev, dT, d_aff + ((size_t)v * B + b) * 16);
+}
+
 }  // namespace afb
 
 using namespace afb;
@@ -391,5 +637,82 @@ extern "C" int afb_embed_bwd(const float* grad_out, const float* x, const float*
     embed_prologue_kernel<<<(B * V + 31) / 32, 32, 0, st>>>(affines, B, V, views);
     dim3 grid((unsigned)((S * S + ETHREADS - 1) / ETHREADS), chunks, B * V);
     embed_bwd_kernel<<<grid, ETHREADS, 0, st>>>(grad_out, x, views, B, V, c, S, ax, d_x, d_affines, acc, counter);
+    return (int)cudaGetLastError();
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// batched entry points: all stages of one pass in one launch each
+// ------------------------------------------------------------------------------------------------
+static int check_batch(int n_stages, const int* c, const int* S, int B, int V) {
+    if (n_stages <= 0 || n_stages > EMAX_STAGES) return AFB_ESHAPE;
+    if (B <= 0 || V <= 0 || (long long)B * V > 65535) return AFB_ESHAPE;
+    for (int i = 0; i < n_stages; ++i)
+        if (c[i] <= 0 || S[i] <= 0 || (long long)S[i] * S[i] * 8 >= 2147483647ll) return AFB_ESHAPE;
+    return AFB_OK;
+}
+
+extern "C" int afb_embed_multi_fwd(int n_stages, const float* const* x, const int* c, const int* S, float* const* out,
+                                   const float* affines, int B, int V, void* workspace, void* stream) {
+    if (!x || !c || !S || !out || !affines || !workspace) return AFB_EINVAL;
+    int rc = check_batch(n_stages, c, S, B, V);
+    if (rc != AFB_OK) return rc;
+    EmbedBatch eb;
+    eb.n = n_stages; eb.B = B; eb.V = V;
+    unsigned long long cta = 0;
+    for (int i = 0; i < n_stages; ++i) {
+        if (!x[i] || !out[i]) return AFB_EINVAL;
+        EmbedStage& sg = eb.st[i];
+        sg.x = x[i]; sg.out = out[i]; sg.go = nullptr; sg.dx = nullptr; sg.c = c[i]; sg.S = S[i]; sg.ch_chunks = 1;
+        // ~64 KB of output per CTA (all channels of its rows), at least one row, at most all rows
+        const long long row_bytes = (long long)c[i] * S[i] * 4;
+        long long rpc = (64 * 1024 + row_bytes - 1) / row_bytes;
+        const long long nrows = (long long)S[i] * S[i];
+        if (rpc < 1) rpc = 1;
+        if (rpc > nrows) rpc = nrows;
+        sg.rows_per_cta = (int)rpc;
+        sg.chunks = (unsigned)((nrows + rpc - 1) / rpc);
+        sg.cta_begin = (unsigned)cta;
+        cta += (unsigned long long)sg.chunks * B * V;
+        if (cta >= 2147483647ull) return AFB_ESHAPE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    EmbedView* views = views_of(workspace, B * V);
+    embed_prologue_kernel<<<(B * V + 31) / 32, 32, 0, st>>>(affines, B, V, views);
+    embed_fwd_fused_kernel<<<(unsigned)cta, ETHREADS, 0, st>>>(eb, views);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int afb_embed_multi_bwd(int n_stages, const float* const* grad_out, const float* const* x, const int* c, const int* S,
+                                   float* const* d_x, const float* affines, int B, int V, float* d_affines, void* workspace,
+                                   void* stream) {
+    if (!grad_out || !x || !c || !S || !affines || !workspace) return AFB_EINVAL;
+    if (!d_x && !d_affines) return AFB_EINVAL;
+    int rc = check_batch(n_stages, c, S, B, V);
+    if (rc != AFB_OK) return rc;
+    EmbedBatch eb;
+    eb.n = 0; eb.B = B; eb.V = V;
+    unsigned long long cta = 0, per_bv = 0;
+    for (int i = 0; i < n_stages; ++i) {
+        if (!grad_out[i]) continue;               // this stage's output took no part in the loss
+        if (!x[i]) return AFB_EINVAL;
+        EmbedStage& sg = eb.st[eb.n++];
+        sg.x = x[i]; sg.out = nullptr; sg.go = grad_out[i]; sg.dx = d_x ? d_x[i] : nullptr; sg.c = c[i]; sg.S = S[i];
+        sg.rows_per_cta = 0;
+        sg.ch_chunks = (c[i] + ECH - 1) / ECH;
+        const unsigned tiles = (unsigned)((S[i] * S[i] + ETHREADS - 1) / ETHREADS);
+        sg.chunks = tiles * (unsigned)sg.ch_chunks;
+        sg.cta_begin = (unsigned)cta;
+        cta += (unsigned long long)sg.chunks * B * V;
+        per_bv += sg.chunks;
+        if (cta >= 2147483647ull) return AFB_ESHAPE;
+    }
+    if (eb.n == 0) return AFB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    double* acc = (double*)workspace;
+    unsigned* counter = (unsigned*)(acc + (size_t)B * V * 16);
+    EmbedView* views = views_of(workspace, B * V);
+    embed_prologue_kernel<<<(B * V + 31) / 32, 32, 0, st>>>(affines, B, V, views);
+    embed_bwd_fused_kernel<<<(unsigned)cta, ETHREADS, 0, st>>>(eb, views, d_affines, acc, counter, (unsigned)per_bv);
     return (int)cudaGetLastError();
 }

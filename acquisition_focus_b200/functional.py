@@ -630,6 +630,69 @@ def r6_to_matrix(ortho: torch.Tensor) -> torch.Tensor:
     return _R6Fn.apply(ortho)
 
 
+def _ptr_array(tensors):
+    return (C.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
+
+
+def _int_array(vals):
+    return (C.c_int * len(vals))(*[int(v) for v in vals])
+
+
+class _EmbedMultiFn(torch.autograd.Function):
+    """(out_0 .. out_{n-1}) = f(affines, x_0 .. x_{n-1}): every stage of one U-Net pass in ONE forward and ONE backward launch."""
+
+    @staticmethod
+    def forward(ctx, affines, V, *xs):
+        n = len(xs)
+        dev = xs[0].device
+        for x in xs:
+            L.require_cuda(x, "x")
+        xd = [x.detach().float().contiguous() for x in xs]
+        ad = affines.detach().to(dev, torch.float32).contiguous()
+        B = xd[0].shape[0]
+        cs = [x.shape[1] // V for x in xd]
+        Ss = [x.shape[2] for x in xd]
+        outs = [torch.empty((B, x.shape[1], S_, S_, S_), dtype=torch.float32, device=dev) for x, S_ in zip(xd, Ss)]
+        lib = L.lib()
+        with torch.cuda.device(dev):
+            ws = torch.empty(int(lib.afb_embed_workspace_bytes(B * V)), dtype=torch.uint8, device=dev)
+            L.check(lib.afb_embed_multi_fwd(n, _ptr_array(xd), _int_array(cs), _int_array(Ss), _ptr_array(outs), L.ptr(ad), B, V,
+                                            L.ptr(ws), L.stream_ptr(dev)), "afb_embed_multi_fwd")
+        ctx.save_for_backward(ad, *xd)
+        ctx.V, ctx.cs, ctx.Ss = V, cs, Ss
+        ctx.x_dtypes, ctx.a_dtype = [x.dtype for x in xs], affines.dtype
+        return tuple(o.to(x.dtype) for o, x in zip(outs, xs))
+
+    @staticmethod
+    def backward(ctx, *gs):
+        ad, *xd = ctx.saved_tensors
+        V, n = ctx.V, len(xd)
+        need_a = ctx.needs_input_grad[0]
+        need_x = [ctx.needs_input_grad[2 + i] for i in range(n)]
+        if not (need_a or any(need_x)) or all(g is None for g in gs):
+            return (None,) * (2 + n)
+        dev = ad.device
+        B = xd[0].shape[0]
+        lib = L.lib()
+        with torch.cuda.device(dev):
+            go = [None if g is None else g.float().contiguous() for g in gs]
+            # every element of dx is written (gather form, no atomics) - but only for stages that received a gradient
+            dxs = [torch.empty_like(x) if (nx and g is not None) else None for x, nx, g in zip(xd, need_x, go)]
+            da = torch.zeros_like(ad) if need_a else None
+            ws = torch.zeros(int(lib.afb_embed_workspace_bytes(B * V)), dtype=torch.uint8, device=dev)
+            L.check(lib.afb_embed_multi_bwd(n, _ptr_array(go), _ptr_array(xd), _int_array(ctx.cs), _int_array(ctx.Ss),
+                                            _ptr_array(dxs) if any(d is not None for d in dxs) else None, L.ptr(ad), B, V, L.ptr(da),
+                                            L.ptr(ws), L.stream_ptr(dev)), "afb_embed_multi_bwd")
+        d_xs = [None if d is None else d.to(dt) for d, dt in zip(dxs, ctx.x_dtypes)]
+        return (da.to(ctx.a_dtype) if da is not None else None, None, *d_xs)
+
+
+def embed_slices_multi(xs, affines: torch.Tensor, n_views: int):
+    """``[SkipConnector.forward(x, affines) for x in xs]`` (models/hybrid_unet.py:40-43: the six encoder skips share the view
+    affines) in ONE launch forward and ONE backward.  ``xs[i]`` ``[B, V*c_i, S_i, S_i]`` -> ``[B, V*c_i, S_i, S_i, S_i]``."""
+    return list(_EmbedMultiFn.apply(affines, n_views, *xs))
+
+
 class _EmbedFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, affines, V):
@@ -670,5 +733,9 @@ class _EmbedFn(torch.autograd.Function):
 def embed_slices(x: torch.Tensor, affines: torch.Tensor, n_views: int) -> torch.Tensor:
     """``SkipConnector.forward`` (models/hybrid_unet.py:71-94).
 
-    x ``[B, V*c, S, S]``, affines ``[V, B, 4, 4]`` (stacked ``b_grid_affines``) -> ``[B, V*c, S, S, S]``."""
-    return _EmbedFn.apply(x, affines, n_views)
+    x ``[B, V*c, S, S]``, affines ``[V, B, 4, 4]`` (stacked ``b_grid_affines``) -> ``[B, V*c, S, S, S]``.
+    Single-pass kernels (zero stream + slab patch of the same rows in one CTA); ``AFB_EMBED_LEGACY=1`` selects the round-1
+    two-kernel forward for A/B measurements."""
+    if os.environ.get("AFB_EMBED_LEGACY", "0") == "1":
+        return _EmbedFn.apply(x, affines, n_views)
+    return _EmbedMultiFn.apply(affines, n_views, x)[0]

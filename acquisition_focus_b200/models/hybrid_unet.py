@@ -20,3 +20,10 @@ class SkipConnector(torch.nn.Module):
         assert C % self.n_views == 0 and len(b_grid_affines) == self.n_views
         affines = torch.stack([ga.to(x.device, self.dtype) for ga in b_grid_affines], dim=0)   # [V,B,4,4]
         return AF.embed_slices(x, affines, self.n_views)
+
+    def embed_all(self, skips, b_grid_affines):
+        """``[self(s, b_grid_affines) for s in skips]`` - what ``HybridUnet.forward`` does with the encoder's skip list
+        (reference ``:40-43``) - as ONE launch forward and ONE backward over all stages."""
+        x0 = skips[0]
+        affines = torch.stack([ga.to(x0.device, self.dtype) for ga in b_grid_affines], dim=0)
+        return AF.embed_slices_multi(list(skips), affines, self.n_views)

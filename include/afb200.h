@@ -245,6 +245,19 @@ int afb_embed_fwd(const float* x, const float* affines, int B, int V, int c, int
 int afb_embed_bwd(const float* grad_out, const float* x, const float* affines, int B, int V, int c,
                   int S, float* d_x, float* d_affines, void* workspace, void* stream);
 
+
+/* All stages of one U-Net pass in one launch each: HybridUnet.forward embeds every encoder skip with the same affines
+ * (models/hybrid_unet.py:40-43: `[self.skip_connector(s, b_grid_affines) for s in skips]`).
+ * x[i] [B, V*c[i], S[i], S[i]], out[i] / grad_out[i] [B, V*c[i], S[i]^3]; n_stages <= 8.  Backward: grad_out[i] == NULL
+ * skips stage i; d_x (array, may be NULL) and its entries may be NULL; d_affines [V,B,4,4] receives the SUM over the stages
+ * (may be NULL).  Same workspace contract as afb_embed_fwd / afb_embed_bwd.  The forward writes every output sector once
+ * (zero stream + slab patch of the same rows inside one CTA). */
+int afb_embed_multi_fwd(int n_stages, const float* const* x, const int* c, const int* S, float* const* out,
+                        const float* affines, int B, int V, void* workspace, void* stream);
+int afb_embed_multi_bwd(int n_stages, const float* const* grad_out, const float* const* x, const int* c, const int* S,
+                        float* const* d_x, const float* affines, int B, int V, float* d_affines, void* workspace,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

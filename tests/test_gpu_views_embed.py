@@ -256,3 +256,40 @@ def test_cuda_graph_replay_matches_eager(afb):
     outs = [t.detach().clone() for t in g()]
     eager = [t.detach().clone() for t in step()]
     close(outs[0], eager[0], 1e-6); close(outs[5], eager[5], 1e-5)
+
+
+def test_embed_all_stages_one_launch_equals_per_stage(afb, monkeypatch):
+    """HybridUnet.forward embeds every encoder skip with the same affines (hybrid_unet.py:40-43): the batched call (one launch
+    forward, one backward, d_affines summed over the stages inside the kernel) against stage-by-stage calls, and the
+    single-pass forward against the round-1 zero-kernel + slab-kernel pair (bitwise)."""
+    V, B = 3, 2
+    stages = [(4, 32), (8, 16), (16, 8), (16, 4), (3, 12)]            # (c, S), incl. a non-multiple-of-4 size
+    case0 = cases.embed_case(32, 4, V, B, seed=91)
+    gas = [a.cuda().requires_grad_(True) for a in case0["affines"]]
+    xs = [cases.randn((B, V * c, S, S), 400 + S).cuda().requires_grad_(True) for c, S in stages]
+    sc = afb.SkipConnector(V)
+    outs = sc.embed_all(xs, gas)
+    gos = [cases.pattern(o.shape, 1.0 + i).cuda() for i, o in enumerate(outs)]
+    torch.autograd.backward(outs, gos)
+    dx_multi = [x.grad.clone() for x in xs]
+    da_multi = torch.stack([a.grad.clone() for a in gas])
+    for x in xs:
+        x.grad = None
+    for a in gas:
+        a.grad = None
+    da_sum = 0
+    for i, x in enumerate(xs):
+        o = sc(x, gas)
+        assert torch.equal(o, outs[i])
+        monkeypatch.setenv("AFB_EMBED_LEGACY", "1")
+        assert torch.equal(sc(x.detach(), [a.detach() for a in gas]), outs[i])
+        monkeypatch.delenv("AFB_EMBED_LEGACY")
+        o.backward(gos[i])
+        assert torch.equal(x.grad, dx_multi[i])
+    da_sum = torch.stack([a.grad for a in gas])
+    close(da_multi, da_sum, 1e-6, "d_affines summed over stages")
+    # a stage whose output takes no part in the loss is skipped, its dx is None / zero
+    xs2 = [x.detach().clone().requires_grad_(True) for x in xs[:2]]
+    o2 = sc.embed_all(xs2, [a.detach() for a in gas])
+    o2[1].backward(gos[1])
+    assert xs2[0].grad is None and torch.equal(xs2[1].grad, dx_multi[1])
