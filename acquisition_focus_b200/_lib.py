@@ -67,6 +67,9 @@ _SIGNATURES = {
     "afb_min_grad_fill": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "afb_slice_fwd": (C.c_int, [C.POINTER(AfbVolume), C.POINTER(AfbViews), C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "afb_slice_fwd3": (C.c_int, [C.POINTER(AfbVolume), C.POINTER(AfbVolume), C.POINTER(AfbVolume), C.POINTER(AfbViews), C.c_int, C.c_int,
+                                  C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]),
     "afb_slice_bwd_workspace_bytes": (C.c_int64, [C.c_int]),
     "afb_slice_bwd": (C.c_int, [C.POINTER(AfbVolume), C.POINTER(AfbViews), C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

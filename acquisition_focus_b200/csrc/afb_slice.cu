@@ -132,6 +132,92 @@ slice_fwd_cl_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad
 }
 
 // ------------------------------------------------------------------------------------------------
+// forward, the three slicings of one acquisition in ONE launch (models/learnable_transform.py:287-306: soft label bilinear,
+// one-hot label nearest, image bilinear with the same pre-affine): the coordinates, corners and weights of an output
+// location are computed once and used for three gathers.  soft: channels-last fp32 (LDG.128 per 4 channels and corner),
+// label: channels-last integers (16-byte vectors, nearest), image: any strides (scalar gathers, loop over its channels).
+// Per-volume arithmetic is the same sequence as slice_fwd_cl_kernel / slice_fwd_kernel: bitwise the same results.
+// ------------------------------------------------------------------------------------------------
+template <typename LT>
+__global__ void __launch_bounds__(NTHREADS, 3)
+slice_fwd3_kernel(VolArgs soft, VolArgs lab, VolArgs img, ViewArgs va, OutGeom g,
+                  int pad_mode_s, float pad_value_s, const float* pad_device_s,
+                  int pad_mode_i, float pad_value_i, const float* pad_device_i,
+                  float* __restrict__ y_soft, LT* __restrict__ y_lab, float* __restrict__ y_img) {
+    const int s = blockIdx.z * va.V + blockIdx.y;
+    const Pix p = pixel_of_thread(g);
+    if (!p.valid) return;
+    const Sample sm = sample_coords(g, p, va, s, soft);              // the three volumes share D, H, W (checked on the host)
+    const int b = blockIdx.z;
+    const int plane = g.Do * g.Ho * g.Wo;
+    const int pix = (p.i * g.Ho + p.j) * g.Wo + p.k;
+    // ---- label: nearest ----
+    if (y_lab) {
+        constexpr int NL = 16 / (int)sizeof(LT);
+        const int xn = __float2int_rn(sm.ix), yn = __float2int_rn(sm.iy), zn = __float2int_rn(sm.iz);
+        const bool in = xn >= 0 && xn < lab.W && yn >= 0 && yn < lab.H && zn >= 0 && zn < lab.D;
+        const LT* __restrict__ src = (const LT*)lab.data + (long long)b * lab.sB;
+        const int off = in ? (zn * (int)lab.sD + yn * (int)lab.sH + xn * (int)lab.sW) : 0;
+        LT* __restrict__ dst = y_lab + (size_t)s * (size_t)(lab.C * plane) + pix;
+        for (int c0 = 0; c0 < lab.C; c0 += NL) {
+            Raw<16> raw = raw_zero<16>();
+            if (in) raw = gather_nc<16>(src + off + c0);
+            const LT* e = reinterpret_cast<const LT*>(raw.w);
+#pragma unroll
+            for (int q = 0; q < NL; ++q) dst[(c0 + q) * plane] = e[q];
+        }
+    }
+    const Corners cn = corners_of(sm, soft);
+    // ---- image: bilinear, generic strides ----
+    if (y_img) {
+        const float pad = pad_of(pad_mode_i, pad_value_i, pad_device_i);
+        const float* __restrict__ src = (const float*)img.data + (long long)b * img.sB;
+        float* __restrict__ dst = y_img + (size_t)s * (size_t)(img.C * plane) + pix;
+        // corner offsets in the image's own strides
+        const int x0 = max(-2, min(__float2int_rd(sm.ix), img.W + 1));
+        const int y0 = max(-2, min(__float2int_rd(sm.iy), img.H + 1));
+        const int z0 = max(-2, min(__float2int_rd(sm.iz), img.D + 1));
+        const int ibase = z0 * (int)img.sD + y0 * (int)img.sH + x0 * (int)img.sW;
+        for (int c = 0; c < img.C; ++c) {
+            const float* __restrict__ sc = src + (long long)c * img.sC;
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int o = ibase + ((k & 1) ? (int)img.sW : 0) + (((k >> 1) & 1) ? (int)img.sH : 0) + ((k >> 2) ? (int)img.sD : 0);
+                v[k] = cn.in(k) ? __ldg(sc + o) : pad;
+            }
+            float acc = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (cn.in(k)) acc = __fadd_rn(acc, __fmul_rn(__fsub_rn(v[k], pad), cn.w(k)));
+            dst[c * plane] = __fadd_rn(acc, pad);
+        }
+    }
+    // ---- soft label: bilinear, channels-last fp32 ----
+    {
+        const float pad = pad_of(pad_mode_s, pad_value_s, pad_device_s);
+        const float* __restrict__ src = (const float*)soft.data + (long long)b * soft.sB;
+        float* __restrict__ dst = y_soft + (size_t)s * (size_t)(soft.C * plane) + pix;
+        for (int c0 = 0; c0 < soft.C; c0 += 4) {
+            float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            Raw<16> raw[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) raw[k] = cn.in(k) ? gather_nc<16>(src + cn.off(k, soft) + c0) : raw_zero<16>();
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (cn.in(k)) {
+                    const float wk = cn.w(k);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        acc[q] = __fadd_rn(acc[q], __fmul_rn(__fsub_rn(__uint_as_float(raw[k].w[q]), pad), wk));
+                }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dst[(c0 + q) * plane] = __fadd_rn(acc[q], pad);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // backward: re-gather, dVolume scatter (RED), dGrid -> 12 sums of dgrid (x) base per slice.
 // CTA reduction (shuffle -> smem) then one fp64 atomic per sum per CTA into the per-slice workspace;
 // view_chain_kernel (afb_views.cu) turns the totals into the gradient of the view input.
@@ -507,5 +593,54 @@ extern "C" int afb_slice_scatter(const afb_volume* vol, const afb_views* views, 
                     vol->sD % 4 == 0 && vol->sB % 4 == 0;
     if (cl) slice_scatter_kernel<true><<<grid, NTHREADS, 0, st>>>(v, a, g, grad_out, d_vol);
     else slice_scatter_kernel<false><<<grid, NTHREADS, 0, st>>>(v, a, g, grad_out, d_vol);
+    return (int)cudaGetLastError();
+}
+
+
+extern "C" int afb_slice_fwd3(const afb_volume* soft, const afb_volume* label, const afb_volume* image, const afb_views* views,
+                              int Do, int Ho, int Wo, int pad_mode_soft, float pad_value_soft, const float* pad_device_soft,
+                              int pad_mode_image, float pad_value_image, const float* pad_device_image,
+                              float* y_soft, void* y_label, float* y_image, void* stream) {
+    VolArgs vs, vl, vi; ViewArgs a, a2;
+    int rc = make_args(soft, views, Do, Ho, Wo, vs, a);
+    if (rc != AFB_OK) return rc;
+    if (!y_soft || soft->dtype != AFB_F32) return soft && soft->dtype != AFB_F32 ? AFB_EDTYPE : AFB_EINVAL;
+    if (channels_last_vec(soft, 4, nullptr, 16) != 16) return AFB_EUNSUPPORTED;      // caller falls back to afb_slice_fwd x3
+    for (int w = 0; w < 2; ++w) {
+        const int pm = w ? pad_mode_image : pad_mode_soft;
+        const float* pd = w ? pad_device_image : pad_device_soft;
+        if (pm < AFB_PAD_ZERO || pm > AFB_PAD_DEVICE || (pm == AFB_PAD_DEVICE && !pd)) return AFB_EINVAL;
+    }
+    vl = vs; vi = vs;
+    if (label) {
+        if (!y_label) return AFB_EINVAL;
+        rc = make_args(label, views, Do, Ho, Wo, vl, a2);
+        if (rc != AFB_OK) return rc;
+        if (label->B != soft->B || label->D != soft->D || label->H != soft->H || label->W != soft->W) return AFB_ESHAPE;
+        const int eb = label->dtype == AFB_I64 ? 8 : label->dtype == AFB_I32 ? 4 : label->dtype == AFB_I16 ? 2 : label->dtype == AFB_U8 ? 1 : 0;
+        if (!eb) return AFB_EDTYPE;
+        if (channels_last_vec(label, eb, nullptr, 16) != 16) return AFB_EUNSUPPORTED;
+    }
+    if (image) {
+        if (!y_image) return AFB_EINVAL;
+        rc = make_args(image, views, Do, Ho, Wo, vi, a2);
+        if (rc != AFB_OK) return rc;
+        if (image->dtype != AFB_F32) return AFB_EUNSUPPORTED;
+        if (image->B != soft->B || image->D != soft->D || image->H != soft->H || image->W != soft->W) return AFB_ESHAPE;
+    }
+    const OutGeom g = make_geom(Do, Ho, Wo);
+    const dim3 grid = slice_grid(g, vs.B, a.V);
+    cudaStream_t st = (cudaStream_t)stream;
+    float* yi = image ? y_image : nullptr;
+#define AFB_F3(LT) slice_fwd3_kernel<LT><<<grid, NTHREADS, 0, st>>>(vs, vl, vi, a, g, pad_mode_soft, pad_value_soft, pad_device_soft, \
+        pad_mode_image, pad_value_image, pad_device_image, y_soft, label ? (LT*)y_label : (LT*)nullptr, yi)
+    switch (label ? label->dtype : AFB_I64) {
+        case AFB_I64: AFB_F3(int64_t); break;
+        case AFB_I32: AFB_F3(int32_t); break;
+        case AFB_I16: AFB_F3(int16_t); break;
+        case AFB_U8: AFB_F3(uint8_t); break;
+        default: return AFB_EDTYPE;
+    }
+#undef AFB_F3
     return (int)cudaGetLastError();
 }

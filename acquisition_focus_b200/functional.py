@@ -214,14 +214,19 @@ class _SliceFn(torch.autograd.Function):
     prepare_views so that several samplings of one acquisition share a single prologue launch."""
 
     @staticmethod
-    def forward(ctx, volume, view_input, spec: ViewSpec, out_size, mode, pad_mode, pad_value, pad_dev, prepared):
+    def forward(ctx, volume, view_input, spec: ViewSpec, out_size, mode, pad_mode, pad_value, pad_dev, prepared, fused=None):
         L.require_cuda(volume, "volume")
         ctx.set_materialize_grads(False)
         if prepared is None:
             spec = spec.with_diff_input(view_input.detach().contiguous())
             prepared = prepare_views(spec, volume.shape[0], volume.shape[2:], out_size, volume.device)
         spec, ga, nii, th = prepared
-        out = _slice_forward_raw(volume.detach(), spec, out_size, mode, pad_mode, pad_value, pad_dev)
+        y_label = y_image = None
+        if fused is not None:          # (label volume | None, image volume | None, image pad triple): ONE launch for all three
+            out, y_label, y_image = _slice_forward3_raw(volume.detach(), fused[0], fused[1], spec, out_size,
+                                                        (pad_mode, pad_value, pad_dev), fused[2])
+        else:
+            out = _slice_forward_raw(volume.detach(), spec, out_size, mode, pad_mode, pad_value, pad_dev)
         ctx.spec, ctx.out_size, ctx.mode = spec, tuple(int(v) for v in out_size), mode
         ctx.pad_mode, ctx.pad_value = pad_mode, pad_value
         ctx.save_for_backward(volume.detach(), pad_dev if pad_dev is not None else torch.empty(0))
@@ -237,13 +242,15 @@ class _SliceFn(torch.autograd.Function):
         ga = ga.clone()          # each Function call owns its differentiable output
         nii = nii if nii is not None else torch.empty(0, device=volume.device)
         th = th if th is not None else torch.empty(0, device=volume.device)
-        ctx.mark_non_differentiable(nii, th)
+        y_label = y_label if y_label is not None else torch.empty(0, device=volume.device)
+        y_image = y_image if y_image is not None else torch.empty(0, device=volume.device)
+        ctx.mark_non_differentiable(nii, th, y_label, y_image)
         if mode == L.NEAREST or not volume.dtype.is_floating_point:
             ctx.mark_non_differentiable(out)
-        return out, ga, nii, th
+        return out, ga, nii, th, y_label, y_image
 
     @staticmethod
-    def backward(ctx, g_out, g_ga, _g_nii, _g_th):
+    def backward(ctx, g_out, g_ga, _g_nii, _g_th, _g_yl=None, _g_yi=None):
         volume, pad_dev = ctx.saved_tensors
         pad_dev = pad_dev if pad_dev.numel() else None
         spec: ViewSpec = ctx.spec
@@ -251,7 +258,7 @@ class _SliceFn(torch.autograd.Function):
         dev = volume.device
         B = volume.shape[0]
         S = B * spec.V
-        none = (None,) * 7
+        none = (None,) * 8
         sample_grad = g_out is not None and ctx.mode == L.BILINEAR and volume.dtype.is_floating_point
         need_vol = ctx.needs_input_grad[0] and sample_grad
         need_aff = ctx.needs_input_grad[1]
@@ -347,7 +354,48 @@ def _run_slice(volume, view_input, spec, out_size, mode, pad, prepared=None):
     if not _is_dense(volume):
         volume = volume.contiguous()
     pad_mode, pad_value, pad_dev = _pad_args(volume, mode, pad)
-    return _SliceFn.apply(volume, view_input, spec, out_size, mode, pad_mode, pad_value, pad_dev, prepared)
+    return _SliceFn.apply(volume, view_input, spec, out_size, mode, pad_mode, pad_value, pad_dev, prepared)[:4]
+
+
+def _fwd3_ok(soft, label, image) -> bool:
+    """Layouts afb_slice_fwd3 takes: fp32 channels-last soft label (C % 4 == 0), channels-last integer label with 16-byte channel
+    vectors, fp32 image; same B, D, H, W."""
+    if soft.dtype != torch.float32 or soft.stride(1) != 1 or soft.shape[1] % 4 != 0 or soft.data_ptr() % 16:
+        return False
+    if any(st % 4 for st in (soft.stride(0), soft.stride(2), soft.stride(3), soft.stride(4))):
+        return False
+    for t in (label, image):
+        if t is not None and (t.shape[0] != soft.shape[0] or tuple(t.shape[2:]) != tuple(soft.shape[2:])):
+            return False
+    if label is not None:
+        if label.dtype not in (torch.int64, torch.int32, torch.int16, torch.uint8) or label.stride(1) != 1:
+            return False
+        n = 16 // label.element_size()
+        if label.shape[1] % n or label.data_ptr() % 16 or any(st % n for st in (label.stride(0), label.stride(2), label.stride(3), label.stride(4))):
+            return False
+    if image is not None and image.dtype != torch.float32:
+        return False
+    return True
+
+
+def _slice_forward3_raw(soft, label, image, spec: ViewSpec, out_size, pad_s, pad_i):
+    """One launch for the soft-label (bilinear), label (nearest) and image (bilinear) slicings of one acquisition."""
+    lib = L.lib()
+    B, Cc = soft.shape[:2]
+    Do, Ho, Wo = (int(v) for v in out_size)
+    dev = soft.device
+    with torch.cuda.device(dev):
+        y_soft = torch.empty((B, spec.V, Cc, Do, Ho, Wo), dtype=torch.float32, device=dev)
+        y_label = torch.empty((B, spec.V, label.shape[1], Do, Ho, Wo), dtype=label.dtype, device=dev) if label is not None else None
+        y_image = torch.empty((B, spec.V, image.shape[1], Do, Ho, Wo), dtype=torch.float32, device=dev) if image is not None else None
+        vs = spec.struct()
+        ds = L.volume_desc(soft)
+        dl = L.volume_desc(label) if label is not None else None
+        di = L.volume_desc(image) if image is not None else None
+        L.check(lib.afb_slice_fwd3(C.byref(ds), C.byref(dl) if dl is not None else None, C.byref(di) if di is not None else None,
+                                   C.byref(vs), Do, Ho, Wo, pad_s[0], float(pad_s[1]), L.ptr(pad_s[2]), pad_i[0], float(pad_i[1]),
+                                   L.ptr(pad_i[2]), L.ptr(y_soft), L.ptr(y_label), L.ptr(y_image), L.stream_ptr(dev)), "afb_slice_fwd3")
+    return y_soft, y_label, y_image
 
 
 # ------------------------------------------------------------------------------------------------
@@ -383,6 +431,7 @@ def slice_with_pre_affine(volume, nii_affine, pre_affine, fov_mm, fov_vox, is_la
 
 
 _SIDE_STREAMS = {}
+_FWD3_DEFAULT = "0"        # set from the B200 measurement (profiles/r2_fwd3_ab.json): one fused launch vs three overlapped launches
 
 
 def _side_stream(dev) -> "torch.cuda.Stream":
@@ -394,7 +443,7 @@ def _side_stream(dev) -> "torch.cuda.Stream":
 
 def acquire_views(x_soft_label, x_label, x_image, nifti_affine, gpre, params, init, *, offset_clip, zoom_clip,
                   spat, slice_fov_mm, slice_fov_vox, soft_pad="global_min", image_pad="global_min", overlap_streams=None,
-                  pad_exchange=None):
+                  pad_exchange=None, fused_forward=None):
     """Fused tail of ``AffineTransformModule.forward`` for all views at once.
 
     x_soft_label ``[B,C,D,H,W]`` float (grad flows), x_label ``[B,C,D,H,W]`` int (nearest, no grad) or None,
@@ -432,6 +481,20 @@ def acquire_views(x_soft_label, x_label, x_image, nifti_affine, gpre, params, in
 
     has_l = x_label is not None and x_label.numel() > 0
     has_i = x_image is not None and x_image.numel() > 0
+    if fused_forward is None:
+        fused_forward = os.environ.get("AFB_FWD3", _FWD3_DEFAULT) == "1"
+    if fused_forward and pad_exchange is None and (has_l or has_i):
+        # ONE launch for the three slicings (coordinates / corners / weights once per output location): the min passes first
+        # (pads), then afb_slice_fwd3.  Falls through to the per-volume launches when a layout does not qualify.
+        xs = x_soft_label if _is_dense(x_soft_label) else x_soft_label.contiguous()
+        xl = (x_label if _is_dense(x_label) else x_label.contiguous()) if has_l else None
+        xi = (x_image.detach() if _is_dense(x_image) else x_image.detach().contiguous()) if has_i else None
+        if _fwd3_ok(xs, xl, xi):
+            pm_s, pv_s, pd_s = _pad_args(xs, L.BILINEAR, soft_pad)
+            pad_i = _pad_args(xi, L.BILINEAR, image_pad) if has_i else (L.PAD_ZERO, 0.0, None)
+            y_soft, ga, nii, theta, y_label, y_image = _SliceFn.apply(xs, p, spec, slice_fov_vox, L.BILINEAR, pm_s, pv_s, pd_s, prepared,
+                                                                      (xl, xi, pad_i))
+            return y_soft, (y_label if has_l else None), (y_image if has_i else None), ga, nii, theta
     if pad_exchange is not None and soft_pad == "global_min" and (not has_i or image_pad == "global_min"):
         # sharded batch: label slicing (needs no pad) on the side stream UNDER the local min passes; then ONE small exchange
         # turns the local pads into whole-batch pads; soft and image slicings follow on the caller's stream

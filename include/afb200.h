@@ -166,6 +166,17 @@ int afb_view_prologue(const afb_views* views, int B, int D, int H, int W, int Do
 int afb_slice_fwd(const afb_volume* vol, const afb_views* views, int Do, int Ho, int Wo, int mode,
                   int pad_mode, float pad_value, const float* pad_device, void* out, void* stream);
 
+/* The three slicings of ONE acquisition in one launch (models/learnable_transform.py:287-306: soft label bilinear, one-hot
+ * label nearest, image bilinear with the same pre-affine): coordinates, corners and weights are computed once per output
+ * location.  soft: fp32, channels-last (sC == 1, C % 4 == 0, 16-byte aligned); label (may be NULL): u8/i16/i32/i64
+ * channels-last with 16-byte channel vectors; image (may be NULL): fp32, any strides.  All three share B, D, H, W.
+ * Results are bitwise those of three afb_slice_fwd calls.  Returns AFB_EUNSUPPORTED when a layout does not qualify (call
+ * afb_slice_fwd per volume instead). */
+int afb_slice_fwd3(const afb_volume* soft, const afb_volume* label, const afb_volume* image, const afb_views* views,
+                   int Do, int Ho, int Wo, int pad_mode_soft, float pad_value_soft, const float* pad_device_soft,
+                   int pad_mode_image, float pad_value_image, const float* pad_device_image,
+                   float* y_soft, void* y_label, float* y_image, void* stream);
+
 /* ---- slice extraction, backward (bilinear only) ----------------------------------------------
  * grad_out         [S,C,Do,Ho,Wo] fp32 contiguous; NULL => chain-only (only grad_grid_affine is
  *                  propagated to d_affine; used for nearest / integer volumes)

@@ -293,3 +293,35 @@ def test_embed_all_stages_one_launch_equals_per_stage(afb, monkeypatch):
     o2 = sc.embed_all(xs2, [a.detach() for a in gas])
     o2[1].backward(gos[1])
     assert xs2[0].grad is None and torch.equal(xs2[1].grad, dx_multi[1])
+
+
+@pytest.mark.parametrize("S", [32, 128])
+def test_fused_three_way_forward_bitwise(afb, S):
+    """afb_slice_fwd3 (soft + label + image slicings of one acquisition in ONE launch) returns bitwise what the three separate
+    launches return, and the backward through it is the same backward."""
+    case = cases.atm_case(S, 2, 3, seed=57)
+    V = case["V"]
+    gpre = torch.stack(case["gpre"], dim=1).cuda()
+    res = []
+    for fused in (False, True):
+        soft = case["soft"].cuda().requires_grad_(True)
+        params = torch.stack(case["params"], dim=1).cuda().requires_grad_(True)
+        out = afb.acquire_views(soft, case["label"].cuda(), case["image"].cuda(), case["nii"].cuda(), gpre, params,
+                                INIT.repeat(V, 1).cuda(), offset_clip=0.2, zoom_clip=0.0, spat=S,
+                                slice_fov_mm=case["slice_fov_mm"].tolist(), slice_fov_vox=case["slice_fov_vox"].tolist(),
+                                fused_forward=fused)
+        (out[0] * cases.pattern(out[0].shape, 1.0).cuda()).sum().backward()
+        res.append((out, soft.grad, params.grad))
+    (a, da_s, da_p), (b, db_s, db_p) = res
+    for x, y in zip(a, b):
+        assert x.dtype == y.dtype and x.shape == y.shape and torch.equal(x, y)
+    close(db_p, da_p, 1e-6, "dparams")
+    close(db_s, da_s, 1e-6, "dsoft")
+    # label-only / image-only combinations
+    soft = case["soft"].cuda()
+    params = torch.stack(case["params"], dim=1).cuda()
+    kw = dict(offset_clip=0.2, zoom_clip=0.0, spat=S, slice_fov_mm=case["slice_fov_mm"].tolist(), slice_fov_vox=case["slice_fov_vox"].tolist())
+    o1 = afb.acquire_views(soft, case["label"].cuda(), None, case["nii"].cuda(), gpre, params, INIT.repeat(V, 1).cuda(), fused_forward=True, **kw)
+    o2 = afb.acquire_views(soft, None, case["image"].cuda(), case["nii"].cuda(), gpre, params, INIT.repeat(V, 1).cuda(), fused_forward=True, **kw)
+    assert torch.equal(o1[0], a[0]) and torch.equal(o1[1], a[1]) and o1[2] is None
+    assert torch.equal(o2[0], a[0]) and torch.equal(o2[2], a[2]) and o2[1] is None
