@@ -93,6 +93,13 @@ _SIGNATURES = {
 }
 
 
+# experiment entries (profiles/ab_*.py only; not part of include/afb200.h)
+_EXPERIMENTS = {
+    "afbx_slice_scatter_priv_probe": (C.c_int, [C.POINTER(AfbVolume), C.POINTER(AfbViews), C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                                 C.c_void_p, C.c_void_p]),
+}
+
+
 def exported_symbols():
     return sorted(_SIGNATURES)
 
@@ -106,7 +113,7 @@ def lib():
                 f"{LIB_PATH} not found - build it with `python -m acquisition_focus_b200.build` "
                 "(there is no CPU fallback for this path)")
         handle = C.CDLL(LIB_PATH)
-        for name, (res, args) in _SIGNATURES.items():
+        for name, (res, args) in list(_SIGNATURES.items()) + list(_EXPERIMENTS.items()):
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args

@@ -16,6 +16,7 @@
 //              L2 atomic sectors than scalar REDs.
 // Per-pixel instruction count matters here (the C = 1 and nearest kernels were issue-bound on coordinate and
 // address arithmetic): no integer or IEEE divisions on the common path, 32-bit offsets, see DESIGN.md section 5.
+#include <cstdlib>
 #include <type_traits>
 
 #include "afb_sampler.cuh"
@@ -266,8 +267,8 @@ slice_bwd_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad_va
 
 // channels-last volumes: VB-byte gathers (LDG.256 for 8 fp32 channels) and 16-byte vector reductions
 // (red.global.add.v4.f32 - the widest vector RED sm_100 has)
-template <typename T, int VB, int BATCH>
-__global__ void __launch_bounds__(NTHREADS, 2)
+template <typename T, int VB, int BATCH, int MINB = 2>
+__global__ void __launch_bounds__(NTHREADS, MINB)
 slice_bwd_cl_kernel(VolArgs vol, ViewArgs va, OutGeom g, int pad_mode, float pad_value, const float* pad_device,
                     const float* __restrict__ grad_out, float* __restrict__ d_vol, float* __restrict__ d_pad,
                     double* __restrict__ ws_acc) {
@@ -363,6 +364,54 @@ slice_scatter_kernel(VolArgs vol, ViewArgs va, OutGeom g, const float* __restric
 #pragma unroll
             for (int k = 0; k < 8; ++k)
                 if (cn.in(k)) atomicAdd(dv + coff + cn.off(k, vol), w[k] * go);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// EXPERIMENT (profiles/ab_kernels.py, not on the product path): shared-memory privatisation of the dVolume scatter.
+// An UPPER BOUND on what privatisation could buy: every corner update is accumulated into a CTA-private table with
+// shared-memory atomics (channel-major layout, so that the lanes of a warp hit different banks), collisions of the
+// direct-mapped table are ignored (two voxels may share a slot: results are WRONG on purpose - the point is the cost of the
+// 64 shared atomics per pixel that any exact scheme also pays), then the table is flushed with coalesced vector REDs.
+// Measured on the B200 against slice_scatter_kernel<true> (16 x red.global.add.v4.f32 per pixel): see DESIGN.md section 5.
+// ------------------------------------------------------------------------------------------------
+constexpr int PRIV_SLOTS = 1024;
+
+__global__ void __launch_bounds__(NTHREADS, 3)
+slice_scatter_priv_probe_kernel(VolArgs vol, ViewArgs va, OutGeom g, const float* __restrict__ grad_out, float* __restrict__ d_vol) {
+    __shared__ float table[8][PRIV_SLOTS];                     // [channel][slot]: 32 KB
+    for (int i = threadIdx.x; i < 8 * PRIV_SLOTS; i += NTHREADS) (&table[0][0])[i] = 0.0f;
+    __syncthreads();
+    const int s = blockIdx.z * va.V + blockIdx.y;
+    const Pix p = pixel_of_thread(g);
+    if (p.valid) {
+        const Sample sm = sample_coords(g, p, va, s, vol);
+        const Corners cn = corners_of(sm, vol);
+        const int plane = g.Do * g.Ho * g.Wo;
+        const float* __restrict__ go_p = grad_out + (size_t)s * (size_t)(vol.C * plane) + ((p.i * g.Ho + p.j) * g.Wo + p.k);
+        float go[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) go[q] = __ldg(go_p + q * plane);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (cn.in(k)) {
+                const float wk = cn.w(k);
+                const unsigned vox = (unsigned)cn.off(k, vol) >> 3;          // voxel index (C = 8 channels-last)
+                const int slot = (int)((vox ^ (vox >> 10) ^ (vox >> 20)) & (PRIV_SLOTS - 1));
+#pragma unroll
+                for (int q = 0; q < 8; ++q) atomicAdd(&table[q][slot], wk * go[q]);
+            }
+    }
+    __syncthreads();
+    // flush: one slot per thread and pass, two 16-byte REDs (coalesced: far cheaper than the real, scattered flush would be)
+    float* __restrict__ dv = d_vol + (long long)blockIdx.z * vol.sB + (size_t)(blockIdx.x % 1024) * PRIV_SLOTS * 8;
+    for (int sl = threadIdx.x; sl < PRIV_SLOTS; sl += NTHREADS) {
+        const float4 a = make_float4(table[0][sl], table[1][sl], table[2][sl], table[3][sl]);
+        const float4 b = make_float4(table[4][sl], table[5][sl], table[6][sl], table[7][sl]);
+        if (a.x != 0.0f || a.y != 0.0f || b.x != 0.0f) {
+            atomicAdd(reinterpret_cast<float4*>(dv + sl * 8), a);
+            atomicAdd(reinterpret_cast<float4*>(dv + sl * 8 + 4), b);
         }
     }
 }
@@ -495,6 +544,13 @@ static int launch_bwd(const afb_volume* vol, const VolArgs& v, const ViewArgs& a
     // LDG.128 x 8 (the earlier kernel): 0.702
     constexpr int WIDE = sizeof(T) >= 4 ? 32 : 16;
 #define AFB_CLB(VB) slice_bwd_cl_kernel<T, VB, 4><<<grid, NTHREADS, 0, st>>>(v, a, g, pad_mode, pad_value, pad_device, grad_out, d_vol, d_pad, acc)
+    // A/B knob for profiles/ab_kernels.py (fp32 only): 1 = <=85 registers / 3 CTAs per SM, 2 = LDG.128 gathers at 3 CTAs per SM
+    const char* ev = getenv("AFB_BWD_VARIANT");
+    const int variant = ev ? atoi(ev) : 0;
+    if (variant != 0 && vb == 32 && std::is_same<T, float>::value) {
+        if (variant == 1) slice_bwd_cl_kernel<T, WIDE, 4, 3><<<grid, NTHREADS, 0, st>>>(v, a, g, pad_mode, pad_value, pad_device, grad_out, d_vol, d_pad, acc);
+        else slice_bwd_cl_kernel<T, 16, 4, 3><<<grid, NTHREADS, 0, st>>>(v, a, g, pad_mode, pad_value, pad_device, grad_out, d_vol, d_pad, acc);
+    } else
     if (vb == 32) AFB_CLB(WIDE);
     else if (vb == 16) AFB_CLB(16);
 #undef AFB_CLB
@@ -642,5 +698,18 @@ extern "C" int afb_slice_fwd3(const afb_volume* soft, const afb_volume* label, c
         default: return AFB_EDTYPE;
     }
 #undef AFB_F3
+    return (int)cudaGetLastError();
+}
+
+
+/* EXPERIMENT entry (not declared in afb200.h): cost of shared-memory privatisation of the scatter, see the kernel's comment. */
+extern "C" int afbx_slice_scatter_priv_probe(const afb_volume* vol, const afb_views* views, int Do, int Ho, int Wo,
+                                             const float* grad_out, float* d_vol, void* stream) {
+    VolArgs v; ViewArgs a;
+    int rc = make_args(vol, views, Do, Ho, Wo, v, a);
+    if (rc != AFB_OK) return rc;
+    if (!grad_out || !d_vol || vol->C != 8 || vol->sC != 1) return AFB_EINVAL;
+    const OutGeom g = make_geom(Do, Ho, Wo);
+    slice_scatter_priv_probe_kernel<<<slice_grid(g, v.B, a.V), NTHREADS, 0, (cudaStream_t)stream>>>(v, a, g, grad_out, d_vol);
     return (int)cudaGetLastError();
 }

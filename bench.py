@@ -511,6 +511,11 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     cpus_per_rank = _pin_to_local_cpus(local, world) if world > 1 else None
     if world > 1:
+        # self-destruct: a collective mismatch must cost minutes, not the GPU box's whole time limit
+        import threading
+        killer = threading.Timer(float(os.environ.get("AFB_BENCH_MAX_SECONDS", "420")), lambda: os._exit(3))
+        killer.daemon = True
+        killer.start()
         _init_dist(dev)
     V = args.views
     if args.scaling == "strong":
@@ -531,7 +536,7 @@ def run_ours(args):
 
     wl = Workload(AF, par, dev, nv, V, seed=1000 + rank, world=world)
     warm = max(3, args.warmup)
-    own, other, own_names = count_own_launches(wl.step, dev) if rank == 0 else (None, None, {})
+    own, other, own_names = count_own_launches(wl.step, dev)      # on EVERY rank: the step contains collectives
     stepper, mode = make_stepper(wl, args.graph == "on", warm)
     for _ in range(warm):
         stepper()

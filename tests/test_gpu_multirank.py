@@ -62,13 +62,15 @@ def _worker(rank, world, port, q):
             (again[4] - dsoft).abs().max().item() <= 1e-6 * dsoft.abs().max().item()
         dist.barrier()
         torch.cuda.synchronize()
-        res = {"rank": rank, "lo": lo, "hi": hi, "pads": [p.cpu() for p in pads], "same_route": same_route}
+        # numpy arrays are pickled by value (torch tensors would travel as shared-memory handles that die with this process)
+        res = {"rank": rank, "lo": lo, "hi": hi, "pads": [p.cpu().numpy() for p in pads], "same_route": same_route}
         if rank == 0:
             dist.destroy_process_group()           # the unsharded run below must not touch a collective
             full = _step(afb, par, case, 0, case["B"])
-            res["full"] = [t.cpu() for t in full[:6]]
-            res["full_pads"] = [p.cpu() for p in full[6]]
-        res.update(ys=ys.cpu(), yl=yl.cpu(), yi=yi.cpu(), ga=ga.cpu(), dsoft=dsoft.cpu(), g=g.cpu())
+            res["full"] = [t.cpu().numpy() for t in full[:6]]
+            res["full_pads"] = [p.cpu().numpy() for p in full[6]]
+        res.update(ys=ys.cpu().numpy(), yl=yl.cpu().numpy(), yi=yi.cpu().numpy(), ga=ga.cpu().numpy(), dsoft=dsoft.cpu().numpy(),
+                   g=g.cpu().numpy())
         q.put(res)
     finally:
         if dist.is_initialized():
@@ -87,6 +89,12 @@ def test_sharded_equals_unsharded_nccl():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    for r in res:                       # back to tensors
+        for k, v in list(r.items()):
+            if isinstance(v, list):
+                r[k] = [torch.from_numpy(x) for x in v]
+            elif hasattr(v, "dtype"):
+                r[k] = torch.from_numpy(v)
     full_ys, full_yl, full_yi, full_ga, full_dsoft, full_dparams = res[0]["full"]
     for a, b in zip(res[0]["pads"], res[0]["full_pads"]):
         assert torch.equal(a, b)                                        # global (min, multiplicity) on every rank
