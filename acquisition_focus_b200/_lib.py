@@ -18,6 +18,7 @@ F32, BF16, F16, I64, I32, I16, U8 = range(7)
 BILINEAR, NEAREST = 0, 1
 PAD_ZERO, PAD_VALUE, PAD_DEVICE = 0, 1, 2
 AFFINE_GRID, AFFINE_PRE, AFFINE_PARAMS = 0, 1, 2
+ROT_ANGLE_AXIS, ROT_NORMAL = 0, 1
 
 DTYPES = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16, torch.int64: I64,
           torch.int32: I32, torch.int16: I16, torch.uint8: U8}
@@ -84,6 +85,11 @@ _SIGNATURES = {
     "afb_embed_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),
     "afb_embed_workspace_bytes": (C.c_int64, [C.c_int]),
+    "afb_compose_pre_affine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "afb_upsample2d_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "afb_upsample2d_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "afb_rot3_fwd": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "afb_rot3_bwd": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "afb_embed_multi_fwd": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_void_p),
                                        C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "afb_embed_multi_bwd": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int),

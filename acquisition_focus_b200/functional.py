@@ -431,7 +431,9 @@ def slice_with_pre_affine(volume, nii_affine, pre_affine, fov_mm, fov_vox, is_la
 
 
 _SIDE_STREAMS = {}
-_FWD3_DEFAULT = "0"        # set from the B200 measurement (profiles/r2_fwd3_ab.json): one fused launch vs three overlapped launches
+# one fused launch vs three launches (label / image overlapped under the min pass on a side stream), measured on the B200 at
+# 64 volumes x 6 views (profiles/r2_ab_fwd3.json): 0.451 vs 0.582 ms stand-alone, 2.726 vs 2.757 ms per whole step
+_FWD3_DEFAULT = "1"
 
 
 def _side_stream(dev) -> "torch.cuda.Stream":
@@ -706,6 +708,7 @@ class _EmbedMultiFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, affines, V, *xs):
+        ctx.set_materialize_grads(False)          # a stage whose output takes no part in the loss is skipped in the backward
         n = len(xs)
         dev = xs[0].device
         for x in xs:
@@ -802,3 +805,89 @@ def embed_slices(x: torch.Tensor, affines: torch.Tensor, n_views: int) -> torch.
     if os.environ.get("AFB_EMBED_LEGACY", "0") == "1":
         return _EmbedFn.apply(x, affines, n_views)
     return _EmbedMultiFn.apply(affines, n_views, x)[0]
+
+
+class _Rot3Fn(torch.autograd.Function):
+    """angle-axis / normal-vector -> homogeneous rotation (utils/transform_utils.py:62-178): one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, params, kind):
+        L.require_cuda(params, "params")
+        p = params.detach().float().contiguous()
+        N = p.shape[0]
+        mat = torch.empty((N, 4, 4), dtype=torch.float32, device=p.device)
+        with torch.cuda.device(p.device):
+            L.check(L.lib().afb_rot3_fwd(int(kind), L.ptr(p), N, L.ptr(mat), L.stream_ptr(p.device)), "afb_rot3_fwd")
+        ctx.save_for_backward(p)
+        ctx.kind, ctx.in_dtype = int(kind), params.dtype
+        return mat.to(params.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        (p,) = ctx.saved_tensors
+        d = torch.empty_like(p)
+        with torch.cuda.device(p.device):
+            L.check(L.lib().afb_rot3_bwd(ctx.kind, L.ptr(p), L.ptr(g.float().contiguous()), p.shape[0], L.ptr(d),
+                                         L.stream_ptr(p.device)), "afb_rot3_bwd")
+        return d.to(ctx.in_dtype), None
+
+
+def angle_axis_to_matrix(angle_axis: torch.Tensor) -> torch.Tensor:
+    """``angle_axis_to_rotation_matrix`` (utils/transform_utils.py:106-178): ``[N,3] -> [N,4,4]``, differentiable."""
+    return _Rot3Fn.apply(angle_axis, L.ROT_ANGLE_AXIS)
+
+
+def normal_to_matrix(normals: torch.Tensor) -> torch.Tensor:
+    """``normal_to_rotation_matrix`` (utils/transform_utils.py:62-103): ``[N,3]`` (columns nz, ny, nx) ``-> [N,4,4]``."""
+    return _Rot3Fn.apply(normals, L.ROT_NORMAL)
+
+
+class _UpsampleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, H, W):
+        L.require_cuda(x, "x")
+        xd = x.detach().float().contiguous()
+        h, w = xd.shape[-3], xd.shape[-2]
+        n = xd.numel() // (h * w)
+        out = torch.empty(xd.shape[:-3] + (H, W, 1), dtype=torch.float32, device=xd.device)
+        with torch.cuda.device(xd.device):
+            L.check(L.lib().afb_upsample2d_fwd(L.ptr(xd), n, h, w, int(H), int(W), L.ptr(out), L.stream_ptr(xd.device)), "afb_upsample2d_fwd")
+        ctx.shape, ctx.HW, ctx.in_dtype = tuple(xd.shape), (int(H), int(W)), x.dtype
+        return out.to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        h, w = ctx.shape[-3], ctx.shape[-2]
+        gd = g.float().contiguous()
+        dx = torch.empty(ctx.shape, dtype=torch.float32, device=gd.device)
+        with torch.cuda.device(gd.device):
+            L.check(L.lib().afb_upsample2d_bwd(L.ptr(gd), dx.numel() // (h * w), h, w, ctx.HW[0], ctx.HW[1], L.ptr(dx),
+                                               L.stream_ptr(gd.device)), "afb_upsample2d_bwd")
+        return dx.to(ctx.in_dtype), None, None
+
+
+def upsample_slices(x: torch.Tensor, size) -> torch.Tensor:
+    """``F.interpolate(x, size=[H, W, 1], mode='trilinear', align_corners=False)`` for one-voxel-thin slices ``[..., h, w, 1]``
+    (the up-sampling of low-resolution slices to the hires in-plane size, running/run_dl.py:193-197); differentiable."""
+    assert x.shape[-1] == 1 and int(size[-1]) == 1, "slices are one voxel thin"
+    return _UpsampleFn.apply(x, int(size[0]), int(size[1]))
+
+
+def compose_pre_affine(base_affine: torch.Tensor, view_affine: torch.Tensor, aug_affine: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``base_affine.inverse() @ view_affine (@ aug_affine)`` -> fp32 ``[B,4,4]`` (running/run_dl.py:227-234 and the augmentation
+    product of :208-223), in fp64 inside one kernel like the reference's fp64 torch chain.  Not differentiable (the reference
+    builds these affines from dataset constants and host-side random draws)."""
+    L.require_cuda(base_affine, "base_affine")
+    dev = base_affine.device
+    base = base_affine.detach().to(torch.float64).contiguous()
+    view = view_affine.detach().to(dev)
+    if view.dtype not in (torch.float32, torch.float64):
+        view = view.float()
+    view = view.contiguous()
+    aug = None if aug_affine is None else aug_affine.detach().to(dev, torch.float32).contiguous()
+    B = base.shape[0]
+    out = torch.empty((B, 4, 4), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.lib().afb_compose_pre_affine(L.ptr(base), L.ptr(view), int(view.dtype == torch.float64), L.ptr(aug), B, L.ptr(out),
+                                               None, L.stream_ptr(dev)), "afb_compose_pre_affine")
+    return out

@@ -15,8 +15,14 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 
+from .. import functional as AF
 from ..utils.nifti_utils import get_zooms, nifti_grid_sample
 from ..utils.transform_utils import get_random_affine
+
+
+def draw_augmentation_affines(B, zoom_strength=0.1, offset_strength=0.1, rotation_strength=0.1, generator=None):
+    """The ``[B,4,4]`` random affines of run_dl.py:208-223 (host RNG, the reference's draw sequence)."""
+    return torch.stack([get_random_affine(rotation_strength, zoom_strength, offset_strength, generator=generator) for _ in range(B)])
 
 
 def apply_affine_augmentation(affine_list, zoom_strength=0.1, offset_strength=0.1, rotation_strength=0.1, generator=None):
@@ -29,12 +35,19 @@ def apply_affine_augmentation(affine_list, zoom_strength=0.1, offset_strength=0.
     return [a @ b_affine.to(a) for a in affine_list]
 
 
-def get_input_affine_for_atm(atm, base_affine, b_view_affines):
-    """run_dl.py:227-234: ``Gpre = base_affine^-1 @ view_affine[view_id]`` (or the module's random affine for 'RND')."""
+def get_input_affine_for_atm(atm, base_affine, b_view_affines, aug_affine=None):
+    """run_dl.py:227-234: ``Gpre = base_affine^-1 @ view_affine[view_id]`` (or the module's random affine for 'RND'); one kernel
+    (fp64 inside, like the reference's fp64 chain) instead of a cuSOLVER LU + matmul; ``aug_affine`` folds the augmentation
+    product of :208-223 into the same launch.  CPU tensors (host-side tests) take the torch expression."""
     B = base_affine.shape[0]
     if atm.view_id == "RND":
-        return atm.random_grid_affine.repeat(B, 1, 1).to(base_affine)
-    return base_affine.inverse() @ torch.as_tensor(b_view_affines[atm.view_id]).view(B, 4, 4).to(base_affine)
+        out = atm.random_grid_affine.repeat(B, 1, 1).to(base_affine)
+        return out if aug_affine is None else out @ aug_affine.to(out)
+    view = torch.as_tensor(b_view_affines[atm.view_id]).view(B, 4, 4)
+    if base_affine.is_cuda:
+        return AF.compose_pre_affine(base_affine, view.to(base_affine.device), aug_affine)
+    out = base_affine.inverse() @ view.to(base_affine)
+    return out if aug_affine is None else out @ aug_affine.to(out)
 
 
 def get_transformed(config, phase, label, soft_label, nifti_affine, grid_affine_pre_mlp, atm, image=None, segment_fn=None):
@@ -58,8 +71,8 @@ def get_transformed(config, phase, label, soft_label, nifti_affine, grid_affine_
             soft_label_slc = label_slc = F.one_hot(pred_slc, num_classes).permute(0, 4, 1, 2, 3).to(soft_label_slc)
     if list(config.slice_fov_vox) != list(config.hires_fov_vox):
         tgt = list(config.hires_fov_vox[:2]) + [1]
-        image_slc = F.interpolate(image_slc, size=tgt, mode="trilinear", align_corners=False)
-        soft_label_slc = F.interpolate(soft_label_slc, size=tgt, mode="trilinear", align_corners=False)
+        image_slc = AF.upsample_slices(image_slc, tgt)             # F.interpolate(..., 'trilinear') of :196-197 as one kernel
+        soft_label_slc = AF.upsample_slices(soft_label_slc, tgt)
     if img_is_invalid:
         image_slc = torch.empty([])
     return image_slc, soft_label_slc, grid_affine
@@ -101,11 +114,12 @@ def get_reconstruction_model_input(batch, phase, config, num_classes, atm_contai
     for atm in atm_container:
         atm.use_affine_theta = config.use_affine_theta
     active = list(atm_container.get_active_view_modules())                            # :269-271
-    input_grid_affines = [get_input_affine_for_atm(m, base_affine, b_view_affines).to(torch.float32) for m in active]
-    if config.do_augment_input_orientation and phase in config.aug_phases:            # :273-278
+    b_aug = None
+    if config.do_augment_input_orientation and phase in config.aug_phases:            # :273-278: ONE draw per batch element
         s = config.sample_augment_strength
-        input_grid_affines = apply_affine_augmentation(input_grid_affines, rotation_strength=0.1 * s, zoom_strength=0.2 * s,
-                                                       offset_strength=0.0, generator=generator)
+        b_aug = draw_augmentation_affines(b_label.shape[0], rotation_strength=0.1 * s, zoom_strength=0.2 * s, offset_strength=0.0,
+                                          generator=generator)
+    input_grid_affines = [get_input_affine_for_atm(m, base_affine, b_view_affines, b_aug).to(torch.float32) for m in active]
 
     # the one-hot-from-index kernels take 2..16 classes (pad value 0 = min of a one-hot needs C >= 2) and <= 65535 slices
     fused = _fused_route_ok(config, active, atm_container) and 2 <= num_classes <= _ONEHOT_MAX_CLASSES and B * len(active) <= 65535
@@ -124,9 +138,8 @@ def get_reconstruction_model_input(batch, phase, config, num_classes, atm_contai
         b_label, num_classes, b_image, nifti_affine, input_grid_affines, mlp_outs=mlp_outs, modules=active, label_out=None)
 
     if list(config.slice_fov_vox) != list(config.hires_fov_vox):                     # :193-197 up-sample low-res slices
-        Bv, V, Cc = y_soft.shape[:3]
         tgt = list(config.hires_fov_vox[:2]) + [1]
-        y_soft = F.interpolate(y_soft.flatten(0, 1), size=tgt, mode="trilinear", align_corners=False).view(Bv, V, Cc, *tgt)
+        y_soft = AF.upsample_slices(y_soft, tgt)                   # all B x V x C planes in one launch
 
     output_grid_affines = [grid_affines[:, v] for v in range(len(active))]
     if config.do_augment_recon_orientation and phase in config.aug_phases:           # :303-309

@@ -257,6 +257,23 @@ int afb_embed_bwd(const float* grad_out, const float* x, const float* affines, i
                   int S, float* d_x, float* d_affines, void* workspace, void* stream);
 
 
+/* ---- callers either side of the samplers ------------------------------------------------------
+ * afb_compose_pre_affine: Gpre[b] = base[b]^-1 @ view[b] (@ aug[b]) - running/run_dl.py:227-234 (+ the augmentation product of
+ *   :208-223), computed in fp64 like the reference (base_affine carries the NIfTI affine's dtype) and rounded once to fp32.
+ *   base [B,4,4] fp64, view [B,4,4] fp32 or fp64, aug [B,4,4] fp32 or NULL, out [B,4,4] fp32; *singular_flag (device int, may be
+ *   NULL) is set to 1 if a base matrix is singular (its output is NaN).
+ * afb_upsample2d_fwd/bwd: F.interpolate(x[N,C,h,w,1], size=[H,W,1], mode='trilinear', align_corners=False) of running/
+ *   run_dl.py:193-197 on n_planes = N*C contiguous [h,w] planes; d_x is fully overwritten (gather form, deterministic).
+ * afb_rot3_fwd/bwd: utils/transform_utils.py:62-178, params [N,3] -> homogeneous [N,4,4]. */
+#define AFB_ROT_ANGLE_AXIS 0
+#define AFB_ROT_NORMAL 1
+int afb_compose_pre_affine(const double* base, const void* view, int view_is_f64, const float* aug, int B, float* out,
+                           int* singular_flag, void* stream);
+int afb_upsample2d_fwd(const float* x, int64_t n_planes, int h, int w, int H, int W, float* out, void* stream);
+int afb_upsample2d_bwd(const float* grad_out, int64_t n_planes, int h, int w, int H, int W, float* d_x, void* stream);
+int afb_rot3_fwd(int kind, const float* params, int N, float* mat, void* stream);
+int afb_rot3_bwd(int kind, const float* params, const float* grad_mat, int N, float* d_params, void* stream);
+
 /* All stages of one U-Net pass in one launch each: HybridUnet.forward embeds every encoder skip with the same affines
  * (models/hybrid_unet.py:40-43: `[self.skip_connector(s, b_grid_affines) for s in skips]`).
  * x[i] [B, V*c[i], S[i], S[i]], out[i] / grad_out[i] [B, V*c[i], S[i]^3]; n_stages <= 8.  Backward: grad_out[i] == NULL

@@ -1,0 +1,75 @@
+"""The small callers either side of the samplers as kernels: rotation parameterisations against the
+reference-minted golden, slice up-sampling against ATen's upsample_trilinear3d (torch CPU), the clinical composition against
+the reference's fp64 torch expression."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import af_oracle as O
+from oracle import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a = torch.as_tensor(a).detach().double().cpu(); b = torch.as_tensor(b).detach().double().cpu()
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+@pytest.mark.parametrize("tag,fn", [("aa", "angle_axis_to_rotation_matrix"), ("nv", "normal_to_rotation_matrix")])
+def test_rotation_parameterisation_kernels_golden(golden_dir, tag, fn):
+    """f4: afb_rot3_fwd/bwd vs utils/transform_utils.py:62-178 (golden minted from the reference; includes r = 0 and |r|^2 < eps)."""
+    from acquisition_focus_b200.utils import transform_utils as T
+    g = np.load(os.path.join(golden_dir, "rotation_params.npz"))
+    x = torch.from_numpy(g[f"{tag}_in"]).cuda().requires_grad_(True)
+    m = getattr(T, fn)(x)
+    assert m.shape == (x.shape[0], 4, 4)
+    e_f = _rel(m, g[f"{tag}_mat"])
+    (m * cases.pattern(m.shape, 1.0).cuda()).sum().backward()
+    e_g = _rel(x.grad, g[f"{tag}_grad"])
+    print(f"{fn}: fwd {e_f:.2e} grad {e_g:.2e}")
+    assert e_f <= 1e-6 and e_g <= 1e-5
+
+
+@pytest.mark.parametrize("shape,size", [((2, 3, 8, 16, 16, 1), (32, 32)), ((4, 8, 32, 32, 1), (128, 128)), ((1, 2, 5, 7, 1), (16, 12)),
+                                        ((2, 2, 16, 16, 1), (16, 16)), ((1, 1, 12, 10, 1), (30, 25))])
+def test_upsample_slices_vs_aten(shape, size):
+    """f3: F.interpolate(x, size=[H,W,1], mode='trilinear', align_corners=False) (running/run_dl.py:193-197): bitwise for the
+    power-of-two ratios the configs use, 1e-6 otherwise; backward against autograd of the same ATen op."""
+    from acquisition_focus_b200 import functional as AF
+    x = cases.randn(shape, 601)
+    tgt = list(size) + [1]
+    xr = x.clone().requires_grad_(True)
+    ref = F.interpolate(xr.flatten(0, -5) if xr.dim() > 5 else xr, size=tgt, mode="trilinear", align_corners=False)
+    xg = x.cuda().requires_grad_(True)
+    out = AF.upsample_slices(xg, tgt)
+    assert tuple(out.shape) == tuple(shape[:-3]) + tuple(tgt)
+    go = cases.pattern(ref.shape, 1.0)
+    (ref * go).sum().backward()
+    (out * go.view(out.shape).cuda()).sum().backward()
+    pow2 = all((o / i) in (1.0, 2.0, 4.0, 8.0) for o, i in zip(size, shape[-3:-1]))
+    if pow2:
+        assert torch.equal(out.detach().cpu().view(ref.shape), ref.detach())
+    assert _rel(out.detach().cpu().view(ref.shape), ref) <= 1e-6
+    assert _rel(xg.grad.cpu(), xr.grad) <= 1e-5
+
+
+def test_compose_pre_affine_vs_reference_expression():
+    """a6: Gpre = base^-1 @ view @ aug (running/run_dl.py:227-234 + :208-223) in one kernel vs the reference's fp64 torch chain."""
+    from acquisition_focus_b200 import functional as AF
+    from acquisition_focus_b200.utils.transform_utils import get_random_affine
+    B = 5
+    gen = torch.Generator().manual_seed(9)
+    base = torch.stack([cases.synthetic.random_aug_affine(gen, 0.4, 0.3, 0.05) for _ in range(B)]).double()
+    base[1, :3, :3] = base[1, :3, :3].flip(0)                      # needs pivoting
+    view = cases.synthetic.phantom_view_affines()["p4CH"][None].repeat(B, 1, 1)
+    torch.manual_seed(3)
+    aug = torch.stack([get_random_affine(0.1, 0.2, 0.0) for _ in range(B)])
+    want = (O.input_affine_for_view(base, view) @ aug.to(base)).float()
+    got = AF.compose_pre_affine(base.cuda(), view.cuda(), aug.cuda())
+    assert got.dtype == torch.float32 and _rel(got, want) <= 2e-7
+    got2 = AF.compose_pre_affine(base.cuda(), view.double().cuda(), None)
+    assert _rel(got2, O.input_affine_for_view(base, view).float()) <= 2e-7
