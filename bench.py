@@ -811,6 +811,8 @@ def kernel_breakdown(AF, dev, soft, label, image, nii, gpre, params, init, go, f
     t = _time(lambda: AF.volume_min(soft, with_mask=True), dev)
     out["volume_min_mask(soft)"] = {"kernel": "volume_min_mask_kernel", "ms": t, "bytes": soft.numel() * 4 + soft.numel() // 8, "bound": "hbm"}
     pad_s, pad_i = AF.volume_min(soft, with_mask=True), AF.volume_min(image)
+    t = _time(lambda: AF.volume_min(image), dev)
+    out["volume_min(image)"] = {"kernel": "volume_min_kernel<float>", "ms": t, "bytes": image.numel() * 4, "bound": "hbm"}
     spec = AF.ViewSpec(kind=L.AFFINE_PARAMS, V=V, gpre=gpre.reshape(nS, 4, 4).contiguous(), init=init, R=R, spat=S,
                        offset_clip=OFFSET_CLIP, zoom_clip=ZOOM_CLIP, nii_affine=nii, fov_mm=tuple(fov_mm),
                        params=params.detach().reshape(nS, NP).contiguous())
@@ -818,12 +820,16 @@ def kernel_breakdown(AF, dev, soft, label, image, nii, gpre, params, init, go, f
     out["view_prologue"] = {"kernel": "view_prologue_kernel", "ms": t, "bytes": nS * (NP * 4 + 64 + 128), "bound": "latency"}
     spec = AF.prepare_views(spec, nv, (S, S, S), fov_vox, dev)[0]
     sd = soft.detach()
+    b_soft, b_lab, b_img = nS * Npix * NUM_CLASSES * 36, nS * Npix * NUM_CLASSES * 16, nS * Npix * 36
+    t = _time(lambda: AF._slice_forward3_raw(sd, label, image, spec, fov_vox, (L.PAD_DEVICE, 0.0, pad_s), (L.PAD_DEVICE, 0.0, pad_i)), dev)
+    out["slice_fwd3(soft C=8 bilinear + label C=8 int64 nearest + image C=1 bilinear, ONE launch)"] = {
+        "kernel": "slice_fwd3_kernel<long>", "ms": t, "bytes": b_soft + b_lab + b_img, "bound": "l2"}
     t = _time(lambda: AF._slice_forward_raw(sd, spec, fov_vox, L.BILINEAR, L.PAD_DEVICE, 0.0, pad_s), dev)
-    out["slice_fwd(soft C=8 bilinear)"] = {"kernel": "slice_fwd_cl_kernel<float, 0", "ms": t, "bytes": nS * Npix * NUM_CLASSES * 36, "bound": "l2"}
+    out["slice_fwd(soft C=8 bilinear) [not in step]"] = {"kernel": "slice_fwd_cl_kernel<float, 0", "ms": t, "bytes": b_soft, "bound": "l2"}
     t = _time(lambda: AF._slice_forward_raw(label, spec, fov_vox, L.NEAREST, L.PAD_ZERO, 0.0, None), dev)
-    out["slice_fwd(label C=8 int64 nearest)"] = {"kernel": "slice_fwd_cl_kernel<long, 1", "ms": t, "bytes": nS * Npix * NUM_CLASSES * 16, "bound": "l2"}
+    out["slice_fwd(label C=8 int64 nearest) [not in step]"] = {"kernel": "slice_fwd_cl_kernel<long, 1", "ms": t, "bytes": b_lab, "bound": "l2"}
     t = _time(lambda: AF._slice_forward_raw(image, spec, fov_vox, L.BILINEAR, L.PAD_DEVICE, 0.0, pad_i), dev)
-    out["slice_fwd(image C=1 bilinear)"] = {"kernel": "slice_fwd_kernel<float, 0>", "ms": t, "bytes": nS * Npix * 36, "bound": "l2"}
+    out["slice_fwd(image C=1 bilinear) [not in step]"] = {"kernel": "slice_fwd_kernel<float, 0>", "ms": t, "bytes": b_img, "bound": "l2"}
     # backward pieces
     d_vol = torch.empty_strided(sd.shape, sd.stride(), dtype=torch.float32, device=dev)
     ws = torch.zeros(int(lib.afb_slice_bwd_workspace_bytes(nS)), dtype=torch.uint8, device=dev)
