@@ -485,13 +485,17 @@ def acquire_views(x_soft_label, x_label, x_image, nifti_affine, gpre, params, in
     has_i = x_image is not None and x_image.numel() > 0
     if fused_forward is None:
         fused_forward = os.environ.get("AFB_FWD3", _FWD3_DEFAULT) == "1"
-    if fused_forward and pad_exchange is None and (has_l or has_i):
+    if fused_forward and (has_l or has_i) and (pad_exchange is None or (soft_pad == "global_min" and (not has_i or image_pad == "global_min"))):
         # ONE launch for the three slicings (coordinates / corners / weights once per output location): the min passes first
         # (pads), then afb_slice_fwd3.  Falls through to the per-volume launches when a layout does not qualify.
         xs = x_soft_label if _is_dense(x_soft_label) else x_soft_label.contiguous()
         xl = (x_label if _is_dense(x_label) else x_label.contiguous()) if has_l else None
         xi = (x_image.detach() if _is_dense(x_image) else x_image.detach().contiguous()) if has_i else None
         if _fwd3_ok(xs, xl, xi):
+            if pad_exchange is not None:     # sharded batch: local min passes, ONE small exchange -> whole-batch pads
+                want_dvol = xs.requires_grad and torch.is_grad_enabled()
+                pads = pad_exchange([volume_min(xs.detach(), with_mask=want_dvol)] + ([volume_min(xi)] if has_i else []))
+                soft_pad, image_pad = pads[0], (pads[1] if has_i else image_pad)
             pm_s, pv_s, pd_s = _pad_args(xs, L.BILINEAR, soft_pad)
             pad_i = _pad_args(xi, L.BILINEAR, image_pad) if has_i else (L.PAD_ZERO, 0.0, None)
             y_soft, ga, nii, theta, y_label, y_image = _SliceFn.apply(xs, p, spec, slice_fov_vox, L.BILINEAR, pm_s, pv_s, pd_s, prepared,

@@ -357,17 +357,42 @@ def _init_dist(dev):
 
 
 def _pin_to_local_cpus(local, world):
-    """N > 1: give each rank its own slice of the host cores (near its GPU's NUMA node when the ranks are spread evenly over the
-    sockets) so that the pinned staging buffers of the e2e leg are first-touched locally.  Best effort."""
+    """N > 1: bind each rank to host cores of ITS GPU's NUMA node (NVML's CPU affinity of the device), split evenly among the
+    ranks that share the node, BEFORE any pinned staging buffer is allocated - so the buffers of the e2e leg are first-touched
+    on the socket the GPU hangs off and the H2D copies do not cross the inter-socket link.  Best effort; returns a description."""
     try:
-        cpus = sorted(os.sched_getaffinity(0))
-        per = max(1, len(cpus) // world)
-        mine = cpus[local * per:(local + 1) * per] or cpus
-        os.sched_setaffinity(0, mine)
-        torch.set_num_threads(max(1, min(len(mine), 8)))
-        return len(mine)
-    except Exception:
-        return None
+        allowed = sorted(os.sched_getaffinity(0))
+        near = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = [int(v) for v in vis.split(",")] if vis and all(v.strip().isdigit() for v in vis.split(",")) else list(range(world))
+            masks = {}
+            for r in range(world):
+                h = pynvml.nvmlDeviceGetHandleByIndex(phys[r] if r < len(phys) else r)
+                words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+                cpus = [w * 64 + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+                masks[r] = tuple(c for c in cpus if c in set(allowed))
+            mine = masks[local]
+            if mine:
+                peers = [r for r in range(world) if masks[r] == mine]          # ranks sharing this NUMA node
+                k = peers.index(local)
+                per = max(1, len(mine) // len(peers))
+                near = list(mine[k * per:(k + 1) * per]) or list(mine)
+        except Exception:
+            near = None
+        if not near:
+            per = max(1, len(allowed) // world)
+            near = allowed[local * per:(local + 1) * per] or allowed
+            how = "even split of the allowed cores (NVML affinity unavailable)"
+        else:
+            how = "NVML CPU affinity of the GPU, split among the ranks on the same NUMA node"
+        os.sched_setaffinity(0, near)
+        torch.set_num_threads(max(1, min(len(near), 8)))
+        return {"cpus": len(near), "first": near[0], "last": near[-1], "how": how}
+    except Exception as e:      # noqa: BLE001
+        return {"error": repr(e)}
 
 
 class Workload:
