@@ -90,6 +90,9 @@ _SIGNATURES = {
     "afb_upsample2d_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "afb_rot3_fwd": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "afb_rot3_bwd": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "afb_peer_buffer_floats": (C.c_int64, [C.c_int, C.c_int]),
+    "afb_peer_collective": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "afb_embed_multi_fwd": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_void_p),
                                        C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "afb_embed_multi_bwd": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int),

@@ -790,6 +790,10 @@ extern "C" int afb_embed_multi_fwd(int n_stages, const float* const* x, const in
             const unsigned long long total4 = (unsigned long long)c[i] * S[i] * S[i] * S[i] / 4;
             sg.nz = (unsigned)((total4 + (unsigned long long)ETHREADS * EZ_F4_PER_THREAD - 1) / ((unsigned long long)ETHREADS * EZ_F4_PER_THREAD));
             sg.ns = (unsigned)(((unsigned long long)S[i] * S[i] * ES_KG + ETHREADS - 1) / ETHREADS);
+            // timing experiments only (results incomplete): run one role alone
+            const char* role = getenv("AFB_EMBED_ROLE");
+            if (role && role[0] == 'z') sg.ns = 0;
+            if (role && role[0] == 's') sg.nz = 0;
             cta += (unsigned long long)(sg.nz + sg.ns) * B * V;
         } else
         cta += (unsigned long long)sg.chunks * B * V;

@@ -564,6 +564,25 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    # N > 1: the three tiny collectives of the step as single-CTA kernels over NVLink peer memory (csrc/afb_peer.cu) instead of
+    # NCCL calls, unless symmetric memory is unavailable on this box or AFB_PEER=0
+    collectives = "none (single GPU)"
+    peer = None
+    if world > 1:
+        collectives = "NCCL (torch.distributed)"
+        if os.environ.get("AFB_PEER", "1") != "0":
+            ok = torch.ones(1, device=dev)
+            try:
+                peer = par.enable_peer_collectives(dev)
+            except Exception as e:      # noqa: BLE001
+                print(f"[bench] rank {rank}: peer-memory collectives unavailable ({e!r}); using NCCL", file=sys.stderr)
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)          # all ranks or none
+            if ok.item() == 1.0:
+                collectives = "afb_peer_collective: own single-CTA kernels over NVLink peer (symmetric) memory"
+            else:
+                par.disable_peer_collectives()
+                peer = None
     shard_ok = selfcheck_sharded(AF, par, dev, rank, world) if world > 1 else None
 
     wl = Workload(AF, par, dev, nv, V, seed=1000 + rank, world=world)
@@ -605,6 +624,8 @@ def run_ours(args):
                 "unit": UNIT, "step_mode": mode2}
         del st2
 
+    if peer is not None:
+        peer.check()                 # a peer that failed to arrive inside any captured / eager exchange raises here
     # All collectives are over: tear the process group down on EVERY rank before any rank-0-only work, so that nothing
     # below can ever wait on a peer (a stray all_reduce here once hung an 8-GPU run until the NCCL watchdog fired).
     if world > 1:
@@ -662,6 +683,7 @@ def run_ours(args):
         line["sharded_equals_unsharded"] = shard_ok
         line["weak_scaling"] = weak
         line["cpus_per_rank"] = cpus_per_rank
+        line["collectives_impl"] = collectives
         line["collectives_per_step"] = ["all_gather 4 floats (whole-batch pads of soft label + image)", "all_reduce 1 float (d out / d pad)",
                                         f"all_reduce [{V},{NP}] fp32 (view-parameter gradients)"]
     print(json.dumps(line))

@@ -274,6 +274,18 @@ int afb_upsample2d_bwd(const float* grad_out, int64_t n_planes, int h, int w, in
 int afb_rot3_fwd(int kind, const float* params, int N, float* mat, void* stream);
 int afb_rot3_bwd(int kind, const float* params, const float* grad_mat, int N, float* d_params, void* stream);
 
+/* ---- the sharded path's collectives over NVLink peer memory -------------------------
+ * One single-CTA kernel: copy the local contribution (optionally summed over `pre_sum` rows of `in`) into this rank's
+ * symmetric buffer, publish the epoch to every peer, wait (bounded, ~2 s, then *err != 0) until every peer has published,
+ * reduce the peers' slots in rank order.  op 0: out[n] = sum over ranks; op 1: out[world*n] = all-gather (rank-major).
+ * bufs_dev: DEVICE array of `world` pointers, entry r = this process' mapping of rank r's buffer of
+ * afb_peer_buffer_floats(n_channels, n_max) floats (symmetric / peer-mapped memory, zeroed before the first call; the host -
+ * e.g. torch.distributed._symmetric_memory - allocates and exchanges the mappings).  epoch: device uint32[n_channels],
+ * zeroed, private to the rank.  Independent exchanges use different channels.  Stream-ordered, CUDA-graph capturable. */
+int64_t afb_peer_buffer_floats(int n_channels, int n_max);
+int afb_peer_collective(void* const* bufs_dev, int rank, int world, int op, int channel, int n_channels, int n, int n_max,
+                        int pre_sum, const float* in, float* out, void* epoch, int* err, void* stream);
+
 /* All stages of one U-Net pass in one launch each: HybridUnet.forward embeds every encoder skip with the same affines
  * (models/hybrid_unet.py:40-43: `[self.skip_connector(s, b_grid_affines) for s in skips]`).
  * x[i] [B, V*c[i], S[i], S[i]], out[i] / grad_out[i] [B, V*c[i], S[i]^3]; n_stages <= 8.  Backward: grad_out[i] == NULL

@@ -63,7 +63,26 @@ def _worker(rank, world, port, q):
         dist.barrier()
         torch.cuda.synchronize()
         # numpy arrays are pickled by value (torch tensors would travel as shared-memory handles that die with this process)
-        res = {"rank": rank, "lo": lo, "hi": hi, "pads": [p.cpu().numpy() for p in pads], "same_route": same_route}
+        # the same exchanges through the NVLink peer-memory kernels (afb_peer_collective) instead of NCCL
+        peer_ok = None
+        try:
+            pc = par.enable_peer_collectives(torch.device("cuda", rank))
+        except Exception as e:      # noqa: BLE001  (symmetric memory unavailable: reported, not failed)
+            pc, peer_ok = None, f"unavailable: {e!r}"
+        if pc is not None:
+            p3 = _step(afb, par, case, lo, hi, via_exchange=True)
+            g3 = par.reduce_view_grads(p3[5])
+            for _ in range(3):                                    # epochs / slot parity over repeated calls
+                g3b = par.reduce_view_grads(p3[5])
+            pc.check()
+            peer_ok = bool(all(torch.equal(a, b) for a, b in zip(p3[:4], (ys, yl, yi, ga)))
+                           and (p3[4] - dsoft).abs().max().item() <= 1e-6 * dsoft.abs().max().item()
+                           and (g3 - g).abs().max().item() <= 1e-6 * g.abs().max().item() and torch.equal(g3, g3b)
+                           and all(torch.equal(a, b) for a, b in zip(p3[6], pads)))
+            par.disable_peer_collectives()
+            dist.barrier()
+            torch.cuda.synchronize()
+        res = {"rank": rank, "lo": lo, "hi": hi, "pads": [p.cpu().numpy() for p in pads], "same_route": same_route, "peer_ok": peer_ok}
         if rank == 0:
             dist.destroy_process_group()           # the unsharded run below must not touch a collective
             full = _step(afb, par, case, 0, case["B"])
@@ -102,6 +121,8 @@ def test_sharded_equals_unsharded_nccl():
     for r in res:
         lo, hi = r["lo"], r["hi"]
         assert r["same_route"]
+        assert r["peer_ok"] is True or (isinstance(r["peer_ok"], str) and r["peer_ok"].startswith("unavailable")), r["peer_ok"]
+        print("peer-memory collectives:", r["peer_ok"])
         assert torch.equal(r["ys"], full_ys[lo:hi]) and torch.equal(r["yl"], full_yl[lo:hi])      # same pad value -> bitwise
         assert torch.equal(r["yi"], full_yi[lo:hi]) and torch.equal(r["ga"], full_ga[lo:hi])
         scale = full_dsoft.abs().max().item()
