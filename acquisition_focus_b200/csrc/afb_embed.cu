@@ -375,12 +375,6 @@ struct EmbedStage {
     unsigned chunks;           // forward: row chunks per (b,v);  backward: pixel tiles x channel chunks per (b,v)
     unsigned cta_begin;        // first CTA of this stage in the flattened grid
     int ch_chunks;             // backward: channel chunks
-    // forward, power-of-two S (role-split path): per (b,v) `nz` CTAs stream zeros over everything EXCEPT the 16-byte groups
-    // near the slab, `ns` CTAs own those groups (zeros and values); the two sets of addresses are disjoint, so the roles
-    // run concurrently (interleaved by blockIdx) and every sector is written exactly once
-    int split;                 // 1: role-split path, 0: zero-then-patch per CTA (any S)
-    int log2S;
-    unsigned nz, ns;
 };
 
 struct EmbedBatch {
@@ -396,113 +390,11 @@ __device__ __forceinline__ int stage_of_cta(const EmbedBatch& eb, unsigned cta) 
     return s;
 }
 
-constexpr int EZ_F4_PER_THREAD = 16;      // zero role: 16-byte stores per thread (64 KB per CTA)
-constexpr int ES_KG = 6;                   // slab role: candidate groups per row laid out in the grid (more: loop)
-
-// Is the 16-byte group (voxels 4*w4 .. 4*w4+3 of row (d,h)) possibly touched by the slab |ix - S/2| < 1 ?  Closed-form
-// coordinates with EXPLICIT fused ops: the zero role and the slab role evaluate this to the same bits, which is what makes
-// their address sets exactly complementary.  thr = 1.1 + 1.5 |t0| (half a group along w plus a 0.1-voxel margin for the
-// difference between the closed form and the bit-exact coordinate code).
-__device__ __forceinline__ bool near_group(const float* __restrict__ t, float a0, float a1, float Sf, float mid, float thr,
-                                           int d, int h, int w4) {
-    const float wc = __fmaf_rn(4.0f, (float)w4, 1.5f);
-    const float g = __fmaf_rn(t[0], __fmaf_rn(a1, wc, a0),
-                              __fmaf_rn(t[1], __fmaf_rn(a1, (float)h, a0), __fmaf_rn(t[2], __fmaf_rn(a1, (float)d, a0), t[3])));
-    const float ix = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.0f), Sf), 1.0f), 0.5f);
-    return fabsf(__fsub_rn(ix, mid)) < thr;
-}
-
-__device__ __forceinline__ void embed_zero_role(const EmbedStage& sg, const float* __restrict__ t, int bv, unsigned zid) {
-    const int S = sg.S, c = sg.c, l2 = sg.log2S;
-    const float Sf = (float)S, mid = (float)(S >> 1), a1 = 2.0f / Sf, a0 = 1.0f / Sf - 1.0f;
-    const float thr = 1.1f + 1.5f * fabsf(t[0]);
-    const size_t S3 = (size_t)S * S * S;
-    const unsigned vol4 = (unsigned)(S3 >> 2);                              // 16-byte groups per channel volume
-    const unsigned long long total4 = (unsigned long long)vol4 * c;         // per (b,v)
-    float4* __restrict__ ob = reinterpret_cast<float4*>(sg.out + (size_t)bv * c * S3);
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const unsigned long long base = (unsigned long long)zid * (ETHREADS * EZ_F4_PER_THREAD);
-    const int l2g = l2 - 2;                                                 // log2(groups per row)
-#pragma unroll 4
-    for (int it = 0; it < EZ_F4_PER_THREAD; ++it) {
-        const unsigned long long i = base + (unsigned long long)it * ETHREADS + threadIdx.x;
-        if (i >= total4) break;
-        const unsigned v4 = (unsigned)(i & (vol4 - 1));
-        const int w4 = (int)(v4 & ((1u << l2g) - 1u));
-        const int h = (int)((v4 >> l2g) & (unsigned)(S - 1));
-        const int d = (int)(v4 >> (l2g + l2));
-        if (!near_group(t, a0, a1, Sf, mid, thr, d, h, w4)) __stcs(ob + i, z4);
-    }
-}
-
-__device__ __forceinline__ void embed_slab_role(const EmbedStage& sg, const float* __restrict__ t, int bv, unsigned sid) {
-    const int S = sg.S, c = sg.c;
-    const float Sf = (float)S, mid = (float)(S >> 1), a1 = 2.0f / Sf, a0 = 1.0f / Sf - 1.0f;
-    const float thr = 1.1f + 1.5f * fabsf(t[0]);
-    const unsigned idx = sid * ETHREADS + threadIdx.x;
-    const unsigned row = idx / ES_KG;
-    const int k0 = (int)(idx - row * ES_KG);
-    if (row >= (unsigned)S * (unsigned)S) return;
-    const int d = (int)(row >> sg.log2S), h = (int)(row & (unsigned)(S - 1));
-    const int G = S >> 2;                                                    // groups per row
-    int lo = 0, hi = G - 1;
-    if (fabsf(t[0]) * Sf >= 0.05f) {
-        // ix(w) = ix0 + t0 w (index units): candidate groups around the crossing, one extra group each side
-        const float g0 = t[0] * a0 + t[1] * (a1 * h + a0) + t[2] * (a1 * d + a0) + t[3];
-        const float ix0 = ((g0 + 1.0f) * Sf - 1.0f) * 0.5f;
-        const float wc = (mid - ix0) / t[0], half = thr / fabsf(t[0]);
-        lo = max(0, (int)floorf((wc - half - 1.5f) * 0.25f) - 1);
-        hi = min(G - 1, (int)ceilf((wc + half - 1.5f) * 0.25f) + 1);
-    }
-    const AxisConst ax = make_axis_dev(S);
-    const float by = base_coord(h, ax), bz = base_coord(d, ax);
-    const size_t S2 = (size_t)S * S, S3 = S2 * S;
-    const float* __restrict__ xs = sg.x + (size_t)bv * c * S2;
-    for (int w4 = lo + k0; w4 <= hi; w4 += ES_KG) {
-        if (!near_group(t, a0, a1, Sf, mid, thr, d, h, w4)) continue;      // the zero role wrote this group
-        Tap tp[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) tp[j] = taps_of(t, base_coord(4 * w4 + j, ax), by, bz, S);
-        float4* __restrict__ o = reinterpret_cast<float4*>(sg.out + (size_t)bv * c * S3 + (size_t)row * S + 4 * w4);
-        const bool any = (tp[0].inb | tp[1].inb | tp[2].inb | tp[3].inb) != 0u;
-#pragma unroll 2
-        for (int ch = 0; ch < c; ++ch) {
-            float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            if (any) {
-                const float* __restrict__ xc = xs + (size_t)ch * S2;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float acc = 0.0f;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if ((tp[j].inb >> q) & 1u) acc = __fadd_rn(acc, __fmul_rn(__ldg(xc + tp[j].off[q]), tp[j].w[q]));
-                    v[j] = acc;
-                }
-            }
-            o[(size_t)ch * (S3 >> 2)] = make_float4(v[0], v[1], v[2], v[3]);
-        }
-    }
-}
-
 __global__ void __launch_bounds__(ETHREADS)
 embed_fwd_fused_kernel(const __grid_constant__ EmbedBatch eb, const EmbedView* __restrict__ views) {
     const int si = stage_of_cta(eb, blockIdx.x);
     const EmbedStage& sg = eb.st[si];
     const unsigned local = blockIdx.x - sg.cta_begin;
-    if (sg.split) {
-        // roles interleaved by CTA index in the ratio ns : nz (Bresenham), so that both make progress together
-        const unsigned per = sg.nz + sg.ns;
-        const int bv = (int)(local / per);
-        const unsigned j = local - (unsigned)bv * per;
-        const unsigned s_before = (unsigned)(((unsigned long long)j * sg.ns) / per);
-        const unsigned s_after = (unsigned)(((unsigned long long)(j + 1) * sg.ns) / per);
-        float tt[12];
-#pragma unroll
-        for (int q = 0; q < 12; ++q) tt[q] = __ldg(views[bv].t + q);
-        if (s_after > s_before) embed_slab_role(sg, tt, bv, s_before);
-        else embed_zero_role(sg, tt, bv, j - s_before);
-        return;
-    }
     const int bv = (int)(local / sg.chunks), chunk = (int)(local - (unsigned)bv * sg.chunks);
     const int S = sg.S, c = sg.c;
     const int nrows = S * S;
@@ -781,21 +673,6 @@ extern "C" int afb_embed_multi_fwd(int n_stages, const float* const* x, const in
         sg.rows_per_cta = (int)rpc;
         sg.chunks = (unsigned)((nrows + rpc - 1) / rpc);
         sg.cta_begin = (unsigned)cta;
-        int l2 = -1;
-        for (int q = 2; q < 12; ++q)
-            if ((1 << q) == S[i]) l2 = q;
-        sg.split = (l2 >= 2 && (((uintptr_t)out[i]) & 15u) == 0 && !getenv("AFB_EMBED_NOSPLIT")) ? 1 : 0;
-        sg.log2S = l2; sg.nz = 0; sg.ns = 0;
-        if (sg.split) {
-            const unsigned long long total4 = (unsigned long long)c[i] * S[i] * S[i] * S[i] / 4;
-            sg.nz = (unsigned)((total4 + (unsigned long long)ETHREADS * EZ_F4_PER_THREAD - 1) / ((unsigned long long)ETHREADS * EZ_F4_PER_THREAD));
-            sg.ns = (unsigned)(((unsigned long long)S[i] * S[i] * ES_KG + ETHREADS - 1) / ETHREADS);
-            // timing experiments only (results incomplete): run one role alone
-            const char* role = getenv("AFB_EMBED_ROLE");
-            if (role && role[0] == 'z') sg.ns = 0;
-            if (role && role[0] == 's') sg.nz = 0;
-            cta += (unsigned long long)(sg.nz + sg.ns) * B * V;
-        } else
         cta += (unsigned long long)sg.chunks * B * V;
         if (cta >= 2147483647ull) return AFB_ESHAPE;
     }

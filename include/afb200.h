@@ -290,8 +290,8 @@ int afb_peer_collective(void* const* bufs_dev, int rank, int world, int op, int 
  * (models/hybrid_unet.py:40-43: `[self.skip_connector(s, b_grid_affines) for s in skips]`).
  * x[i] [B, V*c[i], S[i], S[i]], out[i] / grad_out[i] [B, V*c[i], S[i]^3]; n_stages <= 8.  Backward: grad_out[i] == NULL
  * skips stage i; d_x (array, may be NULL) and its entries may be NULL; d_affines [V,B,4,4] receives the SUM over the stages
- * (may be NULL).  Same workspace contract as afb_embed_fwd / afb_embed_bwd.  The forward writes every output sector once
- * (zero stream + slab patch of the same rows inside one CTA). */
+ * (may be NULL).  Same workspace contract as afb_embed_fwd / afb_embed_bwd.  Forward: a CTA streams zeros over a chunk of
+ * rows of all channels and then patches the slab voxels of the same rows (the patch stores hit lines still dirty in L2). */
 int afb_embed_multi_fwd(int n_stages, const float* const* x, const int* c, const int* S, float* const* out,
                         const float* affines, int B, int V, void* workspace, void* stream);
 int afb_embed_multi_bwd(int n_stages, const float* const* grad_out, const float* const* x, const int* c, const int* S,

@@ -26,10 +26,10 @@ hbm = bench._hbm_peak()[0]
 tot = {"legacy_fwd": 0.0, "single_pass_fwd": 0.0, "per_stage_fwd_bwd": 0.0}
 for (c, S), x, go in zip(stages, xs, gos):
     nb = B * V * c * S ** 3 * 4 + B * V * c * S * S * 4
-    os.environ["AFB_EMBED_LEGACY"] = "1"
-    t_old = bench._time(lambda: afb.embed_slices(x.detach(), aff.detach(), V), dev)
-    os.environ.pop("AFB_EMBED_LEGACY")
-    t_new = bench._time(lambda: afb.embed_slices(x.detach(), aff.detach(), V), dev)
+    t_old = bench._time(lambda: afb.embed_slices(x.detach(), aff.detach(), V), dev)          # zero kernel + slab kernel
+    os.environ["AFB_EMBED_SINGLE_PASS"] = "1"
+    t_new = bench._time(lambda: afb.embed_slices(x.detach(), aff.detach(), V), dev)          # zero-then-patch per CTA
+    os.environ.pop("AFB_EMBED_SINGLE_PASS")
 
     def fb():
         x.grad = None

@@ -25,5 +25,16 @@ for r in ("zero", "slab"):
     os.environ["AFB_EMBED_ROLE"] = r
     res[f"role-split, {r} role only"] = t(lambda: afb.embed_slices(x, aff, V))
 os.environ.pop("AFB_EMBED_ROLE")
+os.environ["AFB_EMBED_ROLE"] = "zero"; os.environ["AFB_EMBED_NOPRED"] = "1"
+res["role-split, zero role only, NO slab test (stores everything)"] = t(lambda: afb.embed_slices(x, aff, V))
+os.environ.pop("AFB_EMBED_ROLE"); os.environ.pop("AFB_EMBED_NOPRED")
+os.environ["AFB_EMBED_NO_PDL"] = "1"; res["role-split, roles back to back (no programmatic dependent launch)"] = t(lambda: afb.embed_slices(x, aff, V)); os.environ.pop("AFB_EMBED_NO_PDL")
+for z, sl in (("2", "2"), ("3", "1"), ("2", "1"), ("4", "1"), ("4", "4"), ("3", "3")):
+    os.environ["AFB_EMBED_ZERO_CTAS_PER_SM"] = z; os.environ["AFB_EMBED_SLAB_CTAS_PER_SM"] = sl
+    res[f"role-split, both roles, {z} zero + {sl} slab CTAs per SM"] = t(lambda: afb.embed_slices(x, aff, V))
+    os.environ["AFB_EMBED_ROLE"] = "slab"
+    res[f"role-split, slab role only, {sl} slab CTAs per SM"] = t(lambda: afb.embed_slices(x, aff, V))
+    os.environ.pop("AFB_EMBED_ROLE")
+os.environ.pop("AFB_EMBED_ZERO_CTAS_PER_SM"); os.environ.pop("AFB_EMBED_SLAB_CTAS_PER_SM")
 os.environ["AFB_EMBED_NOSPLIT"] = "1"; res["zero-then-patch per CTA (v2)"] = t(lambda: afb.embed_slices(x, aff, V)); os.environ.pop("AFB_EMBED_NOSPLIT")
 print(json.dumps({"bytes": nb, "ms": res, "gbs": {k: nb / v / 1e6 for k, v in res.items()}}, indent=1))

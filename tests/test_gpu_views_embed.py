@@ -261,7 +261,7 @@ def test_cuda_graph_replay_matches_eager(afb):
 def test_embed_all_stages_one_launch_equals_per_stage(afb, monkeypatch):
     """HybridUnet.forward embeds every encoder skip with the same affines (hybrid_unet.py:40-43): the batched call (one launch
     forward, one backward, d_affines summed over the stages inside the kernel) against stage-by-stage calls, and the
-    single-pass forward against the round-1 zero-kernel + slab-kernel pair (bitwise)."""
+    single-pass forward (zero-then-patch per CTA) against the zero-kernel + slab-kernel pair of the one-stage call (bitwise)."""
     V, B = 3, 2
     stages = [(4, 32), (8, 16), (16, 8), (16, 4), (3, 12)]            # (c, S), incl. a non-multiple-of-4 size
     case0 = cases.embed_case(32, 4, V, B, seed=91)
@@ -281,9 +281,9 @@ def test_embed_all_stages_one_launch_equals_per_stage(afb, monkeypatch):
     for i, x in enumerate(xs):
         o = sc(x, gas)
         assert torch.equal(o, outs[i])
-        monkeypatch.setenv("AFB_EMBED_LEGACY", "1")
+        monkeypatch.setenv("AFB_EMBED_SINGLE_PASS", "1")                  # one stage through the batched kernels
         assert torch.equal(sc(x.detach(), [a.detach() for a in gas]), outs[i])
-        monkeypatch.delenv("AFB_EMBED_LEGACY")
+        monkeypatch.delenv("AFB_EMBED_SINGLE_PASS")
         o.backward(gos[i])
         assert torch.equal(x.grad, dx_multi[i])
     da_sum = torch.stack([a.grad for a in gas])
