@@ -350,7 +350,23 @@ def _pad_args(volume, mode, pad):
     return pad_mode, pad_value, pad_dev
 
 
+def _maybe_channels_last(volume, spec, out_size):
+    """Planar (NCDHW-contiguous) float volumes with several channels take the generic samplers (a serial channel loop, scalar
+    gathers and scalar atomics); the channels-last kernels move 4-8 channels per instruction.  When a call samples about as
+    many locations as the volume has voxels (3-D -> 3-D resamples, many views) one transposing copy pays for itself:
+    measured on the B200 (bench variant `f1_resample_3d`): 128^3 -> 128^3, C = 8, B = 2: planar 1.9x slower than
+    transpose + channels-last.  Autograd carries the gradient back through the copy."""
+    C_ = volume.shape[1]
+    if volume.dim() != 5 or not volume.dtype.is_floating_point or C_ < 4 or C_ % 4 or volume.stride(1) == 1:
+        return volume
+    n_out = int(out_size[0]) * int(out_size[1]) * int(out_size[2]) * spec.V
+    if 4 * n_out < volume.shape[2] * volume.shape[3] * volume.shape[4] or os.environ.get("AFB_NO_TRANSPOSE", "0") == "1":
+        return volume
+    return volume.contiguous(memory_format=torch.channels_last_3d)
+
+
 def _run_slice(volume, view_input, spec, out_size, mode, pad, prepared=None):
+    volume = _maybe_channels_last(volume, spec, out_size)
     if not _is_dense(volume):
         volume = volume.contiguous()
     pad_mode, pad_value, pad_dev = _pad_args(volume, mode, pad)

@@ -204,6 +204,54 @@ def cfg3_summary(afb, dev, B=2, V=6):
             "all_stages": tot, "hbm_peak_gbs": hbm}
 
 
+def f1_resample_3d(afb, dev, B=2, V=3):
+    """the 3-D -> 3-D resample mode of the same kernels - the prescan resample that feeds the LocalizationNet
+    (models/learnable_transform.py:252-255: nifti_grid_sample(soft label C=8, 128^3 -> 128^3) per view and step, under
+    no_grad), the largest sampler of a training step.  Compulsory HBM bytes: the [B,8,128^3] fp32 output written once + the
+    input read once.  Three routes: channels-last soft volume (what run_dl.py:261-264 hands over), planar soft volume (generic
+    kernel vs one transposing copy + channels-last kernel), and straight from the uint8 label map (no one-hot input at all)."""
+    import json as _json
+    from oracle import cases
+    from oracle import af_oracle as O
+    from acquisition_focus_b200 import functional as AF
+    peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm = float(_json.load(open(peaks))["hbm_gbs"]) if os.path.exists(peaks) else 6650.0
+    S, C = 128, 8
+    case = cases.atm_case(S, B, V, seed=47)
+    soft_cl = case["soft"].to(dev)                                   # channels-last strides (permuted one-hot)
+    soft_pl = soft_cl.contiguous()                                    # planar NCDHW
+    lab = case["lab"].to(dev).to(torch.uint8)
+    nii = case["nii"].to(dev)
+    fov_mm, fov_vox = torch.tensor([192.0] * 3), torch.tensor([S] * 3)
+    out_bytes = B * C * S ** 3 * 4
+    res = {"config": f"f1: prescan resample 128^3 -> 128^3, C=8 bilinear, B={B}, one call per view (V={V} calls per step)", "hbm_peak_gbs": hbm}
+
+    def run(vol):
+        for v in range(V):
+            afb.nifti_grid_sample(vol, nii, target_fov_mm=fov_mm, target_fov_vox=fov_vox, is_label=False, pre_grid_sample_affine=case["gpre"][v].to(dev))
+
+    def run_labels():
+        for v in range(V):
+            AF.onehot_resample_with_pre_affine(lab, nii, case["gpre"][v].to(dev), fov_mm.tolist(), fov_vox.tolist(), C)
+
+    def run_aten():
+        for v in range(V):
+            O.nifti_grid_sample(soft_cl, nii, target_fov_mm=fov_mm.to(dev), target_fov_vox=fov_vox.to(dev), is_label=False,
+                                pre_grid_sample_affine=case["gpre"][v].to(dev))
+    for name, fn, in_bytes in (("channels_last_soft", lambda: run(soft_cl), out_bytes), ("planar_soft_transposed_once", lambda: run(soft_pl), 3 * out_bytes),
+                               ("from_uint8_labels", run_labels, B * S ** 3)):
+        t, _ = timeit(fn, reps=5, warm=2)
+        nb = V * (out_bytes + in_bytes)
+        res[name] = {"ms_per_step": t, "bytes": nb, "gbs": nb / t / 1e6, "frac_of_hbm": nb / t / 1e6 / hbm}
+    os.environ["AFB_NO_TRANSPOSE"] = "1"
+    t, _ = timeit(lambda: run(soft_pl), reps=3, warm=1)
+    os.environ.pop("AFB_NO_TRANSPOSE")
+    res["planar_soft_generic_kernel"] = {"ms_per_step": t, "gbs": V * 2 * out_bytes / t / 1e6}
+    t, _ = timeit(run_aten, reps=2, warm=1)
+    res["aten_cuda_reference_ops"] = {"ms_per_step": t}
+    return res
+
+
 def cfg5(afb, dev):
     out = []
     S, V, C = 256, 16, 8
