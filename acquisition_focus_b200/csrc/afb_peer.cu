@@ -36,6 +36,8 @@ __device__ __forceinline__ float ld_relaxed_sys(const float* p) {
 }
 
 // op 0: out[i] = sum_r in_r[i]      op 1: out[r * n + i] = in_r[i] (all-gather)
+// op 2: n = 2k floats = k (min, multiplicity) pairs -> whole-batch pairs: out[2i] = min_r in_r[2i], out[2i+1] = sum of the
+//       multiplicities of the ranks that hold that minimum (utils/nifti_utils.py:200 under sharding, parallel.allreduce_pad)
 // pre_sum > 1: the local contribution is first summed over `pre_sum` rows of `in` (in[k * n + i]): folds the
 // d_params.sum(0) over the local batch into the collective.
 __global__ void __launch_bounds__(PEER_THREADS)
@@ -70,6 +72,16 @@ peer_collective_kernel(float* const* __restrict__ bufs, int rank, int world, int
             float acc = 0.0f;
             for (int r = 0; r < world; ++r) acc += ld_relaxed_sys(bufs[r] + slot + i);
             out[i] = acc;
+        } else if (op == 2) {
+            if ((i & 1) == 0) {
+                float m = ld_relaxed_sys(bufs[0] + slot + i);
+                for (int r = 1; r < world; ++r) m = fminf(m, ld_relaxed_sys(bufs[r] + slot + i));
+                float cnt = 0.0f;
+                for (int r = 0; r < world; ++r)
+                    if (ld_relaxed_sys(bufs[r] + slot + i) == m) cnt += ld_relaxed_sys(bufs[r] + slot + i + 1);
+                out[i] = m;
+                out[i + 1] = cnt;
+            }
         } else {
             for (int r = 0; r < world; ++r) out[(size_t)r * n + i] = ld_relaxed_sys(bufs[r] + slot + i);
         }
@@ -92,7 +104,8 @@ extern "C" int afb_peer_collective(void* const* bufs_dev, int rank, int world, i
                                    int pre_sum, const float* in, float* out, void* epoch, int* err, void* stream) {
     if (!bufs_dev || !in || !out || !epoch || !err) return AFB_EINVAL;
     if (world <= 0 || world > PEER_MAX_WORLD || rank < 0 || rank >= world || n <= 0 || n > n_max || pre_sum < 1) return AFB_ESHAPE;
-    if (channel < 0 || channel >= n_channels || n_channels * world > PEER_SIGNAL_WORDS || (op != 0 && op != 1)) return AFB_EINVAL;
+    if (channel < 0 || channel >= n_channels || n_channels * world > PEER_SIGNAL_WORDS || op < 0 || op > 2) return AFB_EINVAL;
+    if (op == 2 && (n & 1)) return AFB_ESHAPE;
     peer_collective_kernel<<<1, PEER_THREADS, 0, (cudaStream_t)stream>>>((float* const*)bufs_dev, rank, world, op, channel, n, n_max,
                                                                          pre_sum, in, out, (unsigned*)epoch, err);
     return (int)cudaGetLastError();

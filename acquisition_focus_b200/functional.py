@@ -52,7 +52,7 @@ def _zeros_like_strided(t: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
     return out.zero_()
 
 
-def volume_min(volume: torch.Tensor, with_mask: bool = False) -> torch.Tensor:
+def volume_min(volume: torch.Tensor, with_mask: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``volume.min()`` of nifti_utils.py:200 as a device tensor ``[min, multiplicity]`` (fp32).
 
     ``with_mask`` (fp32 / bf16 / fp16 volumes): the same pass also leaves a 1-bit-per-voxel record of where the minimum sits
@@ -66,7 +66,7 @@ def volume_min(volume: torch.Tensor, with_mask: bool = False) -> torch.Tensor:
     dev = volume.device
     with torch.cuda.device(dev):
         ws = torch.empty(int(lib.afb_volume_min_workspace_bytes()), dtype=torch.uint8, device=dev)
-        out = torch.empty(2, dtype=torch.float32, device=dev)
+        out = torch.empty(2, dtype=torch.float32, device=dev) if out is None else out      # (a row of a caller's [k,2] buffer)
         if with_mask and volume.dtype in (torch.float32, torch.bfloat16, torch.float16):
             mask = torch.empty(int(lib.afb_min_mask_bytes(volume.numel())), dtype=torch.uint8, device=dev)
             if volume.dtype == torch.float32:
@@ -239,7 +239,8 @@ class _SliceFn(torch.autograd.Function):
         # sharded batches (parallel.global_pad): d(out)/d(pad) must be summed over the ranks before it is spread over the minima
         ctx.dpad_reduce = getattr(pad_dev, "_afb_dpad_reduce", None) if pad_dev is not None else None
         ctx.in_dtype = view_input.dtype
-        ga = ga.clone()          # each Function call owns its differentiable output
+        if fused is None:
+            ga = ga.clone()      # several Function calls may share one prologue: each owns its differentiable output
         nii = nii if nii is not None else torch.empty(0, device=volume.device)
         th = th if th is not None else torch.empty(0, device=volume.device)
         y_label = y_label if y_label is not None else torch.empty(0, device=volume.device)
@@ -273,8 +274,11 @@ class _SliceFn(torch.autograd.Function):
             vd, vs = L.volume_desc(volume), spec.struct()
             go = g_out.contiguous().float() if sample_grad else None
             gga = g_ga.contiguous().float() if g_ga is not None else None
-            d_aff = torch.zeros(spec.diff_input().shape, dtype=torch.float32, device=dev) if need_aff else None
-            ws = torch.zeros(int(lib.afb_slice_bwd_workspace_bytes(S)), dtype=torch.uint8, device=dev)
+            # every entry of d_aff is written by the chain kernel; the fp64 accumulators and d_pad share ONE zeroed buffer
+            d_aff = torch.empty(spec.diff_input().shape, dtype=torch.float32, device=dev) if need_aff else None
+            ws_bytes = int(lib.afb_slice_bwd_workspace_bytes(S))
+            zbuf = torch.zeros(ws_bytes + 16, dtype=torch.uint8, device=dev)
+            ws, d_pad0 = zbuf[:ws_bytes], zbuf[ws_bytes:ws_bytes + 4].view(torch.float32)
 
             def theta_half(stream_ptr):      # re-gather + dTheta reduction + analytic chain: does not touch dVolume
                 L.check(lib.afb_slice_bwd(C.byref(vd), C.byref(vs), Do, Ho, Wo, ctx.pad_mode, float(ctx.pad_value), L.ptr(pad_dev),
@@ -297,7 +301,7 @@ class _SliceFn(torch.autograd.Function):
                 if ctx.pad_mode == L.PAD_DEVICE:
                     # MinBackward fused with the zero fill: d_pad first (geometry + grad_out only), then
                     # d_vol = (vol == min) ? d_pad / count : 0, then the scatter adds on top
-                    d_pad = torch.zeros(1, dtype=torch.float32, device=dev)
+                    d_pad = d_pad0
                     L.check(lib.afb_slice_pad_grad(C.byref(vd), C.byref(vs), Do, Ho, Wo, L.ptr(go), L.ptr(d_pad), st),
                             "afb_slice_pad_grad")
                     if ctx.dpad_reduce is not None:
@@ -508,9 +512,25 @@ def acquire_views(x_soft_label, x_label, x_image, nifti_affine, gpre, params, in
         xl = (x_label if _is_dense(x_label) else x_label.contiguous()) if has_l else None
         xi = (x_image.detach() if _is_dense(x_image) else x_image.detach().contiguous()) if has_i else None
         if _fwd3_ok(xs, xl, xi):
-            if pad_exchange is not None:     # sharded batch: local min passes, ONE small exchange -> whole-batch pads
+            if soft_pad == "global_min" and (not has_i or image_pad == "global_min"):
+                # the min passes: the soft volume's (HBM bound, the longest kernel of the forward) on the caller's stream, the
+                # image's UNDER it on the side stream; both write rows of one [k,2] buffer so that a sharded batch turns them
+                # into whole-batch pads with ONE small exchange kernel
                 want_dvol = xs.requires_grad and torch.is_grad_enabled()
-                pads = pad_exchange([volume_min(xs.detach(), with_mask=want_dvol)] + ([volume_min(xi)] if has_i else []))
+                rows = torch.empty((2 if has_i else 1, 2), dtype=torch.float32, device=dev)
+                if has_i and overlap_streams:
+                    main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+                    side.wait_event(main.record_event())
+                    with torch.cuda.stream(side):
+                        pi = volume_min(xi, out=rows[1])
+                    ps = volume_min(xs.detach(), with_mask=want_dvol, out=rows[0])
+                    main.wait_stream(side)
+                else:
+                    ps = volume_min(xs.detach(), with_mask=want_dvol, out=rows[0])
+                    pi = volume_min(xi, out=rows[1]) if has_i else None
+                local = [ps] + ([pi] if has_i else [])
+                local[0]._afb_rows = rows
+                pads = pad_exchange(local) if pad_exchange is not None else local
                 soft_pad, image_pad = pads[0], (pads[1] if has_i else image_pad)
             pm_s, pv_s, pd_s = _pad_args(xs, L.BILINEAR, soft_pad)
             pad_i = _pad_args(xi, L.BILINEAR, image_pad) if has_i else (L.PAD_ZERO, 0.0, None)

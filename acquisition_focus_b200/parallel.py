@@ -75,7 +75,11 @@ def exchange_pads(local, group=None):
     :func:`functional.acquire_views` (which keeps the label slicing overlapped under the min pass)."""
     if not is_distributed():
         return list(local)
-    glob = allreduce_pad(torch.stack(list(local)), group)
+    rows = getattr(local[0], "_afb_rows", None)          # the local pads as rows of ONE [k,2] buffer (functional.acquire_views)
+    if _PEER is not None and group is None and rows is not None and rows.shape[0] == len(local):
+        glob = _PEER.merge_pads(rows)                    # one kernel: publish, wait, min / multiplicity merge
+    else:
+        glob = allreduce_pad(torch.stack(list(local)), group)
     out = []
     for i, loc in enumerate(local):
         g = glob[i].contiguous()
@@ -138,6 +142,12 @@ class PeerCollectives:
         n = rows.shape[1]
         out = torch.empty(n, dtype=torch.float32, device=self.device) if out is None else out
         self._call(0, channel, n, int(pre_sum), rows, out)
+        return out
+
+    def merge_pads(self, rows: torch.Tensor) -> torch.Tensor:
+        """``rows[k, 2]`` local (min, multiplicity) pairs -> the pairs of the whole sharded batch."""
+        out = torch.empty_like(rows)
+        self._call(2, self.CH_PADS, rows.numel(), 1, rows, out)
         return out
 
     def all_gather(self, flat: torch.Tensor, channel: int) -> torch.Tensor:

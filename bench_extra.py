@@ -196,10 +196,29 @@ def cfg3_summary(afb, dev, B=2, V=6):
         tot["aten_fwd_ms"] += rf; tot["aten_fwd_bwd_ms"] += rfbt
         del x, gas, aff, go
         torch.cuda.empty_cache()
-    tot["fwd_gbs"] = tot["bytes_fwd"] / tot["fwd_ms"] / 1e6
+    # all six stages of one U-Net pass in ONE launch each way (HybridUnet.forward embeds every encoder skip with the same affines)
+    case0 = cases.embed_case(128, 16, V, B, seed=300)
+    gas = [a.to(dev).requires_grad_(True) for a in case0["affines"]]
+    cfgs = ((16, 128), (32, 64), (64, 32), (128, 16), (256, 8), (256, 4))
+    xs = [cases.randn((B, V * c, S, S), 500 + S).to(dev).requires_grad_(True) for c, S in cfgs]
+    gos = [torch.randn(B, V * c, S, S, S, device=dev) for c, S in cfgs]
+    xd = [x.detach() for x in xs]
+    affd = torch.stack([g.detach() for g in gas], 0)
+    f1, _ = timeit(lambda: afb.embed_slices_multi(xd, affd, V), reps=5, warm=2)
+
+    def fb_all():
+        for x in xs:
+            x.grad = None
+        for a in gas:
+            a.grad = None
+        torch.autograd.backward(afb.embed_slices_multi(xs, torch.stack(gas, 0), V), gos)
+    fb1, _ = timeit(fb_all, reps=5, warm=2)
+    tot["one_launch_fwd_ms"], tot["one_launch_fwd_bwd_ms"] = f1, fb1
+    tot["fwd_gbs"] = tot["bytes_fwd"] / min(f1, tot["fwd_ms"]) / 1e6
     tot["fwd_frac_of_hbm"] = tot["fwd_gbs"] / hbm
-    tot["value"] = 1e3 / tot["fwd_bwd_ms"]
+    tot["value"] = 1e3 / min(fb1, tot["fwd_bwd_ms"])
     tot["unit"] = "embeddings/s (fwd+bwd, 6 stages, B=2, V=6)"
+    tot["note"] = "fwd_ms / fwd_bwd_ms: stage by stage (zero kernel + slab kernel per stage); one_launch_*: afb_embed_multi_fwd/bwd"
     return {"config": f"cfg3: slice-to-3D embedding, V={V} views, B={B}, six stages (c,S) = (16,128) ... (256,4)", "stages": stages,
             "all_stages": tot, "hbm_peak_gbs": hbm}
 

@@ -277,7 +277,8 @@ int afb_rot3_bwd(int kind, const float* params, const float* grad_mat, int N, fl
 /* ---- the sharded path's collectives over NVLink peer memory -------------------------
  * One single-CTA kernel: copy the local contribution (optionally summed over `pre_sum` rows of `in`) into this rank's
  * symmetric buffer, publish the epoch to every peer, wait (bounded, ~2 s, then *err != 0) until every peer has published,
- * reduce the peers' slots in rank order.  op 0: out[n] = sum over ranks; op 1: out[world*n] = all-gather (rank-major).
+ * reduce the peers' slots in rank order.  op 0: out[n] = sum over ranks; op 1: out[world*n] = all-gather (rank-major);
+ * op 2: n/2 (min, multiplicity) pairs -> the pairs of the whole batch (minimum over ranks, multiplicities of its holders summed).
  * bufs_dev: DEVICE array of `world` pointers, entry r = this process' mapping of rank r's buffer of
  * afb_peer_buffer_floats(n_channels, n_max) floats (symmetric / peer-mapped memory, zeroed before the first call; the host -
  * e.g. torch.distributed._symmetric_memory - allocates and exchanges the mappings).  epoch: device uint32[n_channels],
