@@ -52,7 +52,8 @@ def _zeros_like_strided(t: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
     return out.zero_()
 
 
-def volume_min(volume: torch.Tensor, with_mask: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def volume_min(volume: torch.Tensor, with_mask: bool = False, out: Optional[torch.Tensor] = None,
+               workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``volume.min()`` of nifti_utils.py:200 as a device tensor ``[min, multiplicity]`` (fp32).
 
     ``with_mask`` (fp32 / bf16 / fp16 volumes): the same pass also leaves a 1-bit-per-voxel record of where the minimum sits
@@ -65,8 +66,10 @@ def volume_min(volume: torch.Tensor, with_mask: bool = False, out: Optional[torc
     lib = L.lib()
     dev = volume.device
     with torch.cuda.device(dev):
-        ws = torch.empty(int(lib.afb_volume_min_workspace_bytes()), dtype=torch.uint8, device=dev)
-        out = torch.empty(2, dtype=torch.float32, device=dev) if out is None else out      # (a row of a caller's [k,2] buffer)
+        # (`out`: a row of a caller's [k,2] buffer; `workspace`: pre-allocated by a caller that launches on a side stream -
+        # allocating on a side stream makes the caching allocator pay a cudaMalloc per step)
+        ws = torch.empty(int(lib.afb_volume_min_workspace_bytes()), dtype=torch.uint8, device=dev) if workspace is None else workspace
+        out = torch.empty(2, dtype=torch.float32, device=dev) if out is None else out
         if with_mask and volume.dtype in (torch.float32, torch.bfloat16, torch.float16):
             mask = torch.empty(int(lib.afb_min_mask_bytes(volume.numel())), dtype=torch.uint8, device=dev)
             if volume.dtype == torch.float32:
@@ -176,9 +179,11 @@ def _prep(t: Optional[torch.Tensor], dtype, device) -> Optional[torch.Tensor]:
     return t.detach().to(device=device, dtype=dtype).contiguous()
 
 
-def prepare_views(spec: ViewSpec, B: int, in_size, out_size, device):
+def prepare_views(spec: ViewSpec, B: int, in_size, out_size, device, launch_stream=None):
     """Run the view prologue ONCE for all S = B*V slices (``afb_view_prologue``): returns the spec with its
-    device-side state attached plus ``(grid_affine[B,V,4,4] fp32, nii_affine[B,V,4,4] fp64 | None, theta | None)``."""
+    device-side state attached plus ``(grid_affine[B,V,4,4] fp32, nii_affine[B,V,4,4] fp64 | None, theta | None)``.
+    ``launch_stream``: enqueue the (latency-bound, one warp per slice) kernel there instead of on the current stream - the
+    buffers are still allocated on the current stream and the CALLER joins the streams before anything reads them."""
     lib = L.lib()
     S = B * spec.V
     D, H, W = (int(v) for v in in_size)
@@ -189,8 +194,9 @@ def prepare_views(spec: ViewSpec, B: int, in_size, out_size, device):
         nii = torch.empty((B, spec.V, 4, 4), dtype=torch.float64, device=device) if spec.kind != L.AFFINE_GRID else None
         th = torch.empty((B, spec.V, 4, 4), dtype=torch.float32, device=device) if spec.kind == L.AFFINE_PARAMS else None
         vs = spec.replace(state=None).struct()
-        L.check(lib.afb_view_prologue(C.byref(vs), B, D, H, W, Do, Ho, Wo, L.ptr(state), L.ptr(ga), L.ptr(nii), L.ptr(th),
-                                      L.stream_ptr(device)), "afb_view_prologue")
+        st = L.stream_ptr(device) if launch_stream is None else launch_stream.cuda_stream
+        L.check(lib.afb_view_prologue(C.byref(vs), B, D, H, W, Do, Ho, Wo, L.ptr(state), L.ptr(ga), L.ptr(nii), L.ptr(th), st),
+                "afb_view_prologue")
     return spec.replace(state=state), ga, nii, th
 
 
@@ -490,7 +496,19 @@ def acquire_views(x_soft_label, x_label, x_image, nifti_affine, gpre, params, in
                     fov_mm=tuple(float(v) for v in slice_fov_mm))
     p = params.to(dev, torch.float32).reshape(B * V, NP)
     spec = spec.replace(params=p.detach().contiguous())
-    prepared = prepare_views(spec, B, x_soft_label.shape[2:], slice_fov_vox, dev)      # one prologue for everything below
+    has_l = x_label is not None and x_label.numel() > 0
+    has_i = x_image is not None and x_image.numel() > 0
+    if fused_forward is None:
+        fused_forward = os.environ.get("AFB_FWD3", _FWD3_DEFAULT) == "1"
+    pads_inside = soft_pad == "global_min" and (not has_i or image_pad == "global_min")
+    # one prologue for everything below; when this call also runs the min passes, the prologue (one warp per slice, latency
+    # bound) and the image's min pass go to the side stream UNDER the soft volume's min pass
+    hide = bool(overlap_streams and fused_forward and pads_inside and (has_l or has_i))
+    if hide:
+        main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+        side.wait_event(main.record_event())
+    prepared = prepare_views(spec, B, x_soft_label.shape[2:], slice_fov_vox, dev, launch_stream=side if hide else None)
+    side_joined = not hide
 
     def no_grad_slicings():
         yl = yi = None
@@ -501,10 +519,6 @@ def acquire_views(x_soft_label, x_label, x_image, nifti_affine, gpre, params, in
                 yi = _run_slice(x_image, p.detach(), spec, slice_fov_vox, L.BILINEAR, image_pad, prepared)[0]
         return yl, yi
 
-    has_l = x_label is not None and x_label.numel() > 0
-    has_i = x_image is not None and x_image.numel() > 0
-    if fused_forward is None:
-        fused_forward = os.environ.get("AFB_FWD3", _FWD3_DEFAULT) == "1"
     if fused_forward and (has_l or has_i) and (pad_exchange is None or (soft_pad == "global_min" and (not has_i or image_pad == "global_min"))):
         # ONE launch for the three slicings (coordinates / corners / weights once per output location): the min passes first
         # (pads), then afb_slice_fwd3.  Falls through to the per-volume launches when a layout does not qualify.
@@ -518,13 +532,15 @@ def acquire_views(x_soft_label, x_label, x_image, nifti_affine, gpre, params, in
                 # into whole-batch pads with ONE small exchange kernel
                 want_dvol = xs.requires_grad and torch.is_grad_enabled()
                 rows = torch.empty((2 if has_i else 1, 2), dtype=torch.float32, device=dev)
-                if has_i and overlap_streams:
-                    main, side = torch.cuda.current_stream(dev), _side_stream(dev)
-                    side.wait_event(main.record_event())
-                    with torch.cuda.stream(side):
-                        pi = volume_min(xi, out=rows[1])
+                if hide:
+                    pi = None
+                    if has_i:
+                        ws_i = torch.empty(int(L.lib().afb_volume_min_workspace_bytes()), dtype=torch.uint8, device=dev)   # on `main`
+                        with torch.cuda.stream(side):
+                            pi = volume_min(xi, out=rows[1], workspace=ws_i)
                     ps = volume_min(xs.detach(), with_mask=want_dvol, out=rows[0])
                     main.wait_stream(side)
+                    side_joined = True
                 else:
                     ps = volume_min(xs.detach(), with_mask=want_dvol, out=rows[0])
                     pi = volume_min(xi, out=rows[1]) if has_i else None
@@ -532,11 +548,17 @@ def acquire_views(x_soft_label, x_label, x_image, nifti_affine, gpre, params, in
                 local[0]._afb_rows = rows
                 pads = pad_exchange(local) if pad_exchange is not None else local
                 soft_pad, image_pad = pads[0], (pads[1] if has_i else image_pad)
+            if not side_joined:
+                main.wait_stream(side)
+                side_joined = True
             pm_s, pv_s, pd_s = _pad_args(xs, L.BILINEAR, soft_pad)
             pad_i = _pad_args(xi, L.BILINEAR, image_pad) if has_i else (L.PAD_ZERO, 0.0, None)
             y_soft, ga, nii, theta, y_label, y_image = _SliceFn.apply(xs, p, spec, slice_fov_vox, L.BILINEAR, pm_s, pv_s, pd_s, prepared,
                                                                       (xl, xi, pad_i))
             return y_soft, (y_label if has_l else None), (y_image if has_i else None), ga, nii, theta
+    if not side_joined:                        # (a layout did not qualify for the fused launch)
+        main.wait_stream(side)
+        side_joined = True
     if pad_exchange is not None and soft_pad == "global_min" and (not has_i or image_pad == "global_min"):
         # sharded batch: label slicing (needs no pad) on the side stream UNDER the local min passes; then ONE small exchange
         # turns the local pads into whole-batch pads; soft and image slicings follow on the caller's stream
