@@ -1,6 +1,8 @@
 // afb_sampler.cuh - building blocks shared by the samplers (afb_slice.cu, afb_onehot.cu): thread -> output location
 // mapping, bit-exact coordinates, the 8 trilinear corners, the dgrid (x) base reduction of the backward.
 #pragma once
+#include <cstdlib>
+
 #include "afb_device.cuh"
 
 namespace afb {
@@ -20,6 +22,10 @@ struct OutGeom {
     int rows, cols;             // 2-D view of the output index space: slices (Wo==1): Do x Ho, else (Do*Ho) x Wo
     int tiles_c;
     int tiles_c_shift;          // log2(tiles_c) when it is a power of two, else -1
+    int wide;                   // 1: 3-D outputs with Wo >= 32: a warp covers 32 consecutive w of one row (8 x 32 tile per CTA) so
+                                // that each channel's store is one full 128-byte line; 0: 16 x 16 tile, 8 x 4 warp patch (slices:
+                                // an oblique plane then touches the fewest 128-byte lines per gather instruction)
+    int tile_r, tile_c;
 };
 
 struct Pix {
@@ -30,12 +36,12 @@ struct Pix {
 __device__ __forceinline__ Pix pixel_of_tile(const OutGeom& g, int tile) {
     const int tid = threadIdx.x;
     const int w = tid >> 5, lane = tid & 31;
-    const int lc = ((w & 1) << 3) + (lane & 7);
-    const int lr = ((w >> 1) << 2) + (lane >> 3);
+    const int lc = g.wide ? lane : ((w & 1) << 3) + (lane & 7);
+    const int lr = g.wide ? w : ((w >> 1) << 2) + (lane >> 3);
     int tr, tc;
     if (g.tiles_c_shift >= 0) { tr = tile >> g.tiles_c_shift; tc = tile & (g.tiles_c - 1); }
     else { tr = tile / g.tiles_c; tc = tile - tr * g.tiles_c; }
-    const int row = tr * TILE + lr, col = tc * TILE + lc;
+    const int row = tr * g.tile_r + lr, col = tc * g.tile_c + lc;
     Pix p;
     p.valid = row < g.rows && col < g.cols;
     if (g.Wo == 1) {
@@ -219,7 +225,10 @@ inline OutGeom make_geom(int Do, int Ho, int Wo) {
     g.ax = make_axis(Wo); g.ay = make_axis(Ho); g.az = make_axis(Do);
     g.Do = Do; g.Ho = Ho; g.Wo = Wo;
     if (Wo == 1) { g.rows = Do; g.cols = Ho; } else { g.rows = Do * Ho; g.cols = Wo; }
-    g.tiles_c = (g.cols + TILE - 1) / TILE;
+    g.wide = (Wo >= 32 && !getenv("AFB_NO_WIDE_PATCH")) ? 1 : 0;
+    g.tile_r = g.wide ? NTHREADS / 32 : TILE;
+    g.tile_c = g.wide ? 32 : TILE;
+    g.tiles_c = (g.cols + g.tile_c - 1) / g.tile_c;
     g.tiles_c_shift = -1;
     for (int sh = 0; sh < 31; ++sh)
         if ((1 << sh) == g.tiles_c) g.tiles_c_shift = sh;
@@ -227,7 +236,7 @@ inline OutGeom make_geom(int Do, int Ho, int Wo) {
 }
 
 // (tiles of one slice, views, volumes): slice s = blockIdx.z * V + blockIdx.y, volume b = blockIdx.z
-inline dim3 slice_grid(const OutGeom& g, int B, int V) { return dim3(((g.rows + TILE - 1) / TILE) * g.tiles_c, V, B); }
+inline dim3 slice_grid(const OutGeom& g, int B, int V) { return dim3(((g.rows + g.tile_r - 1) / g.tile_r) * g.tiles_c, V, B); }
 
 
 }  // namespace afb

@@ -266,6 +266,12 @@ def f1_resample_3d(afb, dev, B=2, V=3):
     t, _ = timeit(lambda: run(soft_pl), reps=3, warm=1)
     os.environ.pop("AFB_NO_TRANSPOSE")
     res["planar_soft_generic_kernel"] = {"ms_per_step": t, "gbs": V * 2 * out_bytes / t / 1e6}
+    os.environ["AFB_NO_WIDE_PATCH"] = "1"            # A/B: the slices' 8 x 4 warp patch instead of 32 x 1 rows for 3-D outputs
+    t, _ = timeit(lambda: run(soft_cl), reps=5, warm=2)
+    t2, _ = timeit(run_labels, reps=5, warm=2)
+    os.environ.pop("AFB_NO_WIDE_PATCH")
+    res["channels_last_soft_narrow_patch"] = {"ms_per_step": t}
+    res["from_uint8_labels_narrow_patch"] = {"ms_per_step": t2}
     t, _ = timeit(run_aten, reps=2, warm=1)
     res["aten_cuda_reference_ops"] = {"ms_per_step": t}
     return res
