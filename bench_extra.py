@@ -223,7 +223,7 @@ def cfg3_summary(afb, dev, B=2, V=6):
             "all_stages": tot, "hbm_peak_gbs": hbm}
 
 
-def f1_resample_3d(afb, dev, B=2, V=3):
+def f1_resample_3d(afb, dev, B=8, V=3):
     """the 3-D -> 3-D resample mode of the same kernels - the prescan resample that feeds the LocalizationNet
     (models/learnable_transform.py:252-255: nifti_grid_sample(soft label C=8, 128^3 -> 128^3) per view and step, under
     no_grad), the largest sampler of a training step.  Compulsory HBM bytes: the [B,8,128^3] fp32 output written once + the
@@ -243,7 +243,17 @@ def f1_resample_3d(afb, dev, B=2, V=3):
     nii = case["nii"].to(dev)
     fov_mm, fov_vox = torch.tensor([192.0] * 3), torch.tensor([S] * 3)
     out_bytes = B * C * S ** 3 * 4
-    res = {"config": f"f1: prescan resample 128^3 -> 128^3, C=8 bilinear, B={B}, one call per view (V={V} calls per step)", "hbm_peak_gbs": hbm}
+    res = {"config": f"f1: prescan resample 128^3 -> 128^3, C=8 bilinear, B={B}, one call per view (V={V} calls per step; B=2 is "
+                     "host-launch bound: 0.35 ms per call for ~0.1 ms of kernels)", "hbm_peak_gbs": hbm}
+    # the sampler kernel alone (one launch, no min pass / prologue / wrapper), channels-last soft volume
+    from acquisition_focus_b200 import _lib as L
+    spec = AF.ViewSpec(kind=L.AFFINE_PRE, V=1, nii_affine=case["nii"].to(dev), fov_mm=(192.0, 192.0, 192.0), pre=case["gpre"][0].to(dev).contiguous())
+    spec = AF.prepare_views(spec, B, (S, S, S), [S, S, S], dev)[0]
+    pad0 = AF.volume_min(case["soft"].to(dev))
+    sd = case["soft"].to(dev)
+    t, _ = timeit(lambda: AF._slice_forward_raw(sd, spec, [S, S, S], L.BILINEAR, L.PAD_DEVICE, 0.0, pad0), reps=5, warm=2)
+    res["kernel_only_channels_last"] = {"ms": t, "bytes": 2 * B * C * S ** 3 * 4, "gbs": 2 * B * C * S ** 3 * 4 / t / 1e6,
+                                        "frac_of_hbm": 2 * B * C * S ** 3 * 4 / t / 1e6 / hbm}
 
     def run(vol):
         for v in range(V):
