@@ -12,6 +12,7 @@ Layout
 from . import functional  # noqa: F401
 from .functional import (acquire_views, acquire_views_from_labels, affine_grid_sample, embed_slices,  # noqa: F401
                          embed_slices_multi, r6_to_matrix, slice_with_pre_affine, volume_min)
+from .clinical_cardiac_views import get_clinical_cardiac_view_affines  # noqa: F401
 from .models.hybrid_unet import SkipConnector  # noqa: F401
 from .models.learnable_transform import AffineTransformModule, ATModulesContainer  # noqa: F401
 from .utils.nifti_utils import nifti_grid_sample  # noqa: F401

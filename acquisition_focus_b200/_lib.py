@@ -93,6 +93,9 @@ _SIGNATURES = {
     "afb_peer_buffer_floats": (C.c_int64, [C.c_int, C.c_int]),
     "afb_peer_collective": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "afb_label_group_moments": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "afb_label_extent_search": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_void_p, C.c_void_p, C.c_double,
+                                           C.c_void_p, C.c_void_p]),
     "afb_embed_multi_fwd": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_void_p),
                                        C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "afb_embed_multi_bwd": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int),

@@ -274,3 +274,133 @@ extern "C" int afb_rot3_bwd(int kind, const float* params, const float* grad_mat
     rot3_bwd_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(kind, params, grad_mat, N, d_params);
     return (int)cudaGetLastError();
 }
+
+// ------------------------------------------------------------------------------------------------
+// f4 (rest): the voxel passes of get_clinical_cardiac_view_affines (functional/clinical_cardiac_views.py:223-364), which the
+// reference runs on sparse CPU tensors: (1) count / first / second moments of the voxel index cloud of several label GROUPS
+// in ONE pass over the integer label map (exact 64-bit integer sums -> centre and inertia tensor of
+// utils/torch_sparse_tensor_utils.py:34-56), (2) the bisection search for the extent of a group along an axis (:36-60).
+// The 3x3 eigenproblems and the frame algebra in between are a few dozen flops and stay on the host, as in the reference.
+// ------------------------------------------------------------------------------------------------
+namespace afb {
+
+constexpr int MOM_THREADS = 256;
+constexpr int MOM_MAX_GROUPS = 8;
+
+template <typename L>
+__global__ void __launch_bounds__(MOM_THREADS)
+label_group_moments_kernel(const L* __restrict__ lab, int D, int H, int W, const unsigned* __restrict__ masks, int G,
+                           unsigned long long* __restrict__ out /*[G][10]*/) {
+    __shared__ unsigned long long red[MOM_THREADS / 32][10];
+    const long long n = (long long)D * H * W;
+    unsigned gm[MOM_MAX_GROUPS];
+#pragma unroll
+    for (int g = 0; g < MOM_MAX_GROUPS; ++g) gm[g] = g < G ? masks[g] : 0u;
+    for (int g = 0; g < G; ++g) {
+        unsigned long long s[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (long long i = (long long)blockIdx.x * MOM_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * MOM_THREADS) {
+            const long long l = (long long)lab[i];
+            if (l <= 0 || l > 31 || !((gm[g] >> l) & 1u)) continue;
+            const unsigned long long w = (unsigned long long)(i % W), h = (unsigned long long)((i / W) % H), d = (unsigned long long)(i / ((long long)W * H));
+            s[0] += 1; s[1] += d; s[2] += h; s[3] += w;
+            s[4] += d * d; s[5] += d * h; s[6] += d * w; s[7] += h * h; s[8] += h * w; s[9] += w * w;
+        }
+        const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+        for (int q = 0; q < 10; ++q) {
+            unsigned long long v = s[q];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) red[wi][q] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < 10) {
+            unsigned long long t = 0;
+            for (int ww = 0; ww < MOM_THREADS / 32; ++ww) t += red[ww][threadIdx.x];
+            if (t) atomicAdd(out + g * 10 + threadIdx.x, t);
+        }
+        __syncthreads();
+    }
+}
+
+// bisection of get_extent_vect (:36-48) for +dir and -dir, one CTA: fact in fp64 like the reference's Python floats, the end
+// point and the distances in fp32 like its tensors; out[0], out[1] = the returned factors ((start+end)/2) for +dir / -dir.
+constexpr int EXT_THREADS = 1024;
+
+template <typename L>
+__global__ void __launch_bounds__(EXT_THREADS)
+label_extent_search_kernel(const L* __restrict__ lab, int D, int H, int W, unsigned mask, const float* __restrict__ center,
+                           const float* __restrict__ dir, double init_end, double* __restrict__ out) {
+    __shared__ float red[EXT_THREADS / 32];
+    __shared__ float dmin_s;
+    const long long n = (long long)D * H * W;
+    const float MIN_DIST = (float)(1.73 / 2.0);
+    for (int sgn = 0; sgn < 2; ++sgn) {
+        const float dd = sgn ? -dir[0] : dir[0], dh = sgn ? -dir[1] : dir[1], dw = sgn ? -dir[2] : dir[2];
+        double start = 0.0, end = init_end;
+        while ((end - start) > 1.73 / 2.0) {
+            const double new_end = end - (end - start) / 2.0;
+            const float f = (float)new_end;
+            const float ed = __fadd_rn(center[0], __fmul_rn(f, dd)), eh = __fadd_rn(center[1], __fmul_rn(f, dh)),
+                        ew = __fadd_rn(center[2], __fmul_rn(f, dw));
+            float best = INFINITY;
+            for (long long i = threadIdx.x; i < n; i += EXT_THREADS) {
+                const long long l = (long long)lab[i];
+                if (l <= 0 || l > 31 || !((mask >> l) & 1u)) continue;
+                const float w = (float)(i % W), h = (float)((i / W) % H), d = (float)(i / ((long long)W * H));
+                const float a = __fsub_rn(d, ed), b = __fsub_rn(h, eh), c = __fsub_rn(w, ew);
+                const float r = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fmul_rn(c, c)));
+                best = fminf(best, r);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                float m = red[0];
+                for (int q = 1; q < EXT_THREADS / 32; ++q) m = fminf(m, red[q]);
+                dmin_s = m;
+            }
+            __syncthreads();
+            if (dmin_s > MIN_DIST) end = new_end;
+            else start += (end - start) / 2.0;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out[sgn] = (start + end) / 2.0;
+    }
+}
+
+}  // namespace afb
+
+extern "C" int afb_label_group_moments(const void* labels, int dtype, int D, int H, int W, const unsigned* group_masks_dev, int n_groups,
+                                       unsigned long long* out_dev /*[n_groups][10], zeroed by the caller*/, void* stream) {
+    if (!labels || !group_masks_dev || !out_dev) return AFB_EINVAL;
+    if (D <= 0 || H <= 0 || W <= 0 || n_groups <= 0 || n_groups > MOM_MAX_GROUPS) return AFB_ESHAPE;
+    const long long n = (long long)D * H * W;
+    long long want = (n + MOM_THREADS - 1) / MOM_THREADS;
+    const unsigned grid = (unsigned)(want > 148 * 8 ? 148 * 8 : want);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case AFB_U8: label_group_moments_kernel<uint8_t><<<grid, MOM_THREADS, 0, st>>>((const uint8_t*)labels, D, H, W, group_masks_dev, n_groups, out_dev); break;
+        case AFB_I16: label_group_moments_kernel<int16_t><<<grid, MOM_THREADS, 0, st>>>((const int16_t*)labels, D, H, W, group_masks_dev, n_groups, out_dev); break;
+        case AFB_I32: label_group_moments_kernel<int32_t><<<grid, MOM_THREADS, 0, st>>>((const int32_t*)labels, D, H, W, group_masks_dev, n_groups, out_dev); break;
+        case AFB_I64: label_group_moments_kernel<int64_t><<<grid, MOM_THREADS, 0, st>>>((const int64_t*)labels, D, H, W, group_masks_dev, n_groups, out_dev); break;
+        default: return AFB_EDTYPE;
+    }
+    return (int)cudaGetLastError();
+}
+
+extern "C" int afb_label_extent_search(const void* labels, int dtype, int D, int H, int W, unsigned group_mask, const float* center_dev,
+                                       const float* dir_dev, double init_end, double* out_dev /*[2]*/, void* stream) {
+    if (!labels || !center_dev || !dir_dev || !out_dev) return AFB_EINVAL;
+    if (D <= 0 || H <= 0 || W <= 0 || !(init_end > 0.0)) return AFB_ESHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case AFB_U8: label_extent_search_kernel<uint8_t><<<1, EXT_THREADS, 0, st>>>((const uint8_t*)labels, D, H, W, group_mask, center_dev, dir_dev, init_end, out_dev); break;
+        case AFB_I16: label_extent_search_kernel<int16_t><<<1, EXT_THREADS, 0, st>>>((const int16_t*)labels, D, H, W, group_mask, center_dev, dir_dev, init_end, out_dev); break;
+        case AFB_I32: label_extent_search_kernel<int32_t><<<1, EXT_THREADS, 0, st>>>((const int32_t*)labels, D, H, W, group_mask, center_dev, dir_dev, init_end, out_dev); break;
+        case AFB_I64: label_extent_search_kernel<int64_t><<<1, EXT_THREADS, 0, st>>>((const int64_t*)labels, D, H, W, group_mask, center_dev, dir_dev, init_end, out_dev); break;
+        default: return AFB_EDTYPE;
+    }
+    return (int)cudaGetLastError();
+}

@@ -274,6 +274,19 @@ int afb_upsample2d_bwd(const float* grad_out, int64_t n_planes, int h, int w, in
 int afb_rot3_fwd(int kind, const float* params, int N, float* mat, void* stream);
 int afb_rot3_bwd(int kind, const float* params, const float* grad_mat, int N, float* d_params, void* stream);
 
+/* The voxel passes of get_clinical_cardiac_view_affines (functional/clinical_cardiac_views.py:223-364; sparse CPU tensors in
+ * the reference).  labels: contiguous [D,H,W] integer label map (values 1..31 take part).  A GROUP is a bit mask over label
+ * values (bit l set <=> label l belongs to it).
+ * afb_label_group_moments: for each of n_groups (<= 8) groups the exact integer sums {count, sum d, sum h, sum w, sum dd, dh,
+ *   dw, hh, hw, ww} of the voxel indices (-> centre and inertia tensor, utils/torch_sparse_tensor_utils.py:34-56), one pass;
+ *   out [n_groups][10] uint64, zeroed by the caller.
+ * afb_label_extent_search: get_min_max_extent_along_axis (:51-62): bisection for the extent of the group along +dir and -dir
+ *   from `center` (fp64 factors, fp32 distances like the reference); out[0], out[1] = the two factors. */
+int afb_label_group_moments(const void* labels, int dtype, int D, int H, int W, const unsigned* group_masks_dev, int n_groups,
+                            unsigned long long* out_dev, void* stream);
+int afb_label_extent_search(const void* labels, int dtype, int D, int H, int W, unsigned group_mask, const float* center_dev,
+                            const float* dir_dev, double init_end, double* out_dev, void* stream);
+
 /* ---- the sharded path's collectives over NVLink peer memory -------------------------
  * One single-CTA kernel: copy the local contribution (optionally summed over `pre_sum` rows of `in`) into this rank's
  * symmetric buffer, publish the epoch to every peer, wait (bounded, ~2 s, then *err != 0) until every peer has published,

@@ -72,3 +72,44 @@ def test_compose_pre_affine_vs_reference_expression():
     assert got.dtype == torch.float32 and _rel(got, want) <= 2e-7
     got2 = AF.compose_pre_affine(base.cuda(), view.double().cuda(), None)
     assert _rel(got2, O.input_affine_for_view(base, view).float()) <= 2e-7
+
+
+def test_clinical_cardiac_view_affines_on_gpu(monkeypatch):
+    """f4: get_clinical_cardiac_view_affines (functional/clinical_cardiac_views.py:223-364) with its voxel passes as CUDA kernels
+    (group moments, extent bisection, nearest slices through the sampler) against the affines the REFERENCE minted for the same
+    phantom (data/phantom_view_affines.json), and - other size, 5 SA slices, uint8 / int64 label maps - against the same host
+    logic driven by numpy / oracle restatements of the three device passes."""
+    from acquisition_focus_b200 import clinical_cardiac_views as CV
+    from oracle.clinical_np import cpu_extent as _cpu_extent, cpu_moments as _cpu_moments
+    syn = cases.synthetic
+    lab = torch.from_numpy(syn.heart_phantom(128))
+    nii = torch.diag(torch.tensor([1.5, 1.5, 1.5, 1.0]))
+    got = CV.get_clinical_cardiac_view_affines(lab.cuda(), nii, syn.CLASS_DICT, num_sa_slices=3, return_unrolled=True)
+    want = syn.phantom_view_affines()
+    assert list(got.keys()) == list(want.keys())
+    worst = max((got[k] - want[k]).abs().max().item() for k in want)
+    print(f"clinical views vs reference-minted golden: max abs diff {worst:.2e}")
+    assert worst <= 2e-5
+    # the device passes themselves against their restatements
+    lab64 = torch.from_numpy(np.ascontiguousarray(np.roll(syn.heart_phantom(64), 3, axis=1)))
+    masks = [CV._group_mask((1, 3)), CV._group_mask((1, 2, 3)), CV._group_mask(syn.CLASS_DICT.values())]
+    for dt in (torch.uint8, torch.int64):
+        c1, m1, i1 = CV._moments(lab64.to(dt).cuda(), masks)
+        c2, m2, i2 = _cpu_moments(lab64, masks)
+        assert np.array_equal(c1, c2) and torch.equal(m1, m2) and torch.equal(i1, i2)          # exact integer moments
+    d = torch.tensor([0.48, -0.6, 0.64])
+    d = d / d.norm()
+    p1, p2 = CV._extent_along_axis(lab64.to(torch.uint8).cuda(), masks[0], m1[0], d)
+    q1, q2 = _cpu_extent(lab64, masks[0], m1[0], d)
+    assert torch.allclose(p1, q1, atol=1e-6) and torch.allclose(p2, q2, atol=1e-6)
+    nii64 = torch.diag(torch.tensor([3.0, 3.0, 3.0, 1.0]))
+    g5 = CV.get_clinical_cardiac_view_affines(lab64.cuda(), nii64, syn.CLASS_DICT, num_sa_slices=5)
+    monkeypatch.setattr(CV, "_moments", _cpu_moments)
+    monkeypatch.setattr(CV, "_extent_along_axis", _cpu_extent)
+    monkeypatch.setattr(CV, "nifti_grid_sample", O.nifti_grid_sample)
+    import acquisition_focus_b200._lib as L
+    monkeypatch.setattr(L, "require_cuda", lambda *a, **k: None)
+    w5 = CV.get_clinical_cardiac_view_affines(lab64, nii64, syn.CLASS_DICT, num_sa_slices=5)
+    for k in w5:
+        a, b = (torch.stack(g5[k]), torch.stack(w5[k])) if k == "ALL_SA" else (g5[k], w5[k])
+        assert (a - b).abs().max().item() <= 1e-6, k
