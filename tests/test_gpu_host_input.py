@@ -124,3 +124,32 @@ def test_half_dvolume_cast_is_round_to_nearest_even(afb, dt):
     out = torch.empty_like(x, dtype=dt)
     L.check(L.lib().afb_cast_from_f32(L.ptr(x), L.ptr(out), L.DTYPES[dt], x.numel(), L.stream_ptr(x.device)), "cast")
     assert torch.equal(out, x.to(dt))
+
+
+def test_double_buffered_pipeline_equals_single_upload(afb):
+    """HostInputPipeline (next batch uploaded + expanded while the current one is used; slots reused two submits later) hands
+    over, batch after batch, bitwise what upload_one_hot returns, also when a slow consumer delays the slot release."""
+    from acquisition_focus_b200.running.host_input import HostInputPipeline, upload_one_hot
+    C, B, S = 8, 4, 32
+    batches = []
+    for k in range(5):
+        lab = cases.randint(0, C, (B, S, S, S), 700 + k).pin_memory()
+        img = cases.randn((B, 1, S, S, S), 800 + k).pin_memory()
+        batches.append((lab, img))
+    pipe = HostInputPipeline(C, "cuda", depth=2, group_volumes=2)
+    pipe.submit(*batches[0])
+    spin = torch.empty(64 * 1024 * 1024, device="cuda")
+    for k in range(5):
+        if k + 1 < 5:
+            pipe.submit(*batches[k + 1])
+        db = pipe.get()
+        got = [db.label_map.clone(), db.label.clone(), db.soft_label.clone(), db.image.clone(), db.soft_pad.clone(), db.image_pad.clone()]
+        for _ in range(3):
+            spin.add_(1.0)                      # the consumer keeps the compute stream busy before it releases the slot
+        chk = db.soft_label.sum()               # ... and still reads the slot afterwards
+        pipe.release(db)
+        ref = upload_one_hot(batches[k][0], batches[k][1], C, "cuda", group_volumes=2)
+        want = [ref.label_map, ref.label, ref.soft_label, ref.image, ref.soft_pad, ref.image_pad]
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
+        assert chk.item() == ref.soft_label.sum().item()
