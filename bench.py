@@ -655,7 +655,8 @@ def run_ours(args):
         import bench_extra as BX
         import acquisition_focus_b200 as afb_pkg
         for name, fn in (("cfg1_single_slice", BX.cfg1), ("cfg2_default_batch", BX.cfg2), ("cfg3_embedding", BX.cfg3_summary),
-                         ("cfg5_256_stress", BX.cfg5), ("f1_resample_3d", BX.f1_resample_3d)):
+                         ("cfg5_256_stress", BX.cfg5), ("f1_resample_3d", BX.f1_resample_3d),
+                         ("f4_clinical_views", BX.f4_clinical_views)):
             try:
                 variants[name] = fn(afb_pkg, dev)
             except Exception as e:      # noqa: BLE001

@@ -287,6 +287,39 @@ def f1_resample_3d(afb, dev, B=8, V=3):
     return res
 
 
+def f4_clinical_views(afb, dev):
+    """SURVEY 8 f4 (last item): get_clinical_cardiac_view_affines (functional/clinical_cardiac_views.py:223-364) on the 128^3
+    phantom: the GPU drop-in (voxel passes as kernels, 3x3 eigenproblems on the host) next to the reference's own function on
+    the host cores (sparse CPU tensors; the vendored unmodified code when oracle/_ref travelled, else not timed)."""
+    import time
+    from acquisition_focus_b200 import synthetic as syn
+    lab = torch.from_numpy(syn.heart_phantom(128))
+    nii = torch.diag(torch.tensor([1.5, 1.5, 1.5, 1.0]))
+    lab_d = lab.to(dev).to(torch.uint8)
+    fn = lambda: afb.get_clinical_cardiac_view_affines(lab_d, nii, syn.CLASS_DICT, num_sa_slices=3, return_unrolled=True)
+    for _ in range(2):
+        got = fn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        fn()
+    torch.cuda.synchronize()
+    ours = (time.perf_counter() - t0) / 5 * 1e3
+    res = {"config": "f4: clinical cardiac view affines (10 views) from a 128^3 label map", "ms_wall": ours,
+           "note": "wall clock incl. six small D2H reads and the host eigenproblems; 8 kernel launches"}
+    try:
+        import bench
+        R = bench._load_vendored_reference()
+        if R is not None:
+            t0 = time.perf_counter()
+            want = R.get_clinical_cardiac_view_affines(lab, nii, syn.CLASS_DICT, num_sa_slices=3, return_unrolled=True)
+            res["reference_cpu_ms_wall"] = (time.perf_counter() - t0) * 1e3
+            res["max_abs_diff_vs_reference"] = max((got[k] - want[k]).abs().max().item() for k in want)
+    except Exception as e:      # noqa: BLE001
+        res["reference_cpu_error"] = repr(e)
+    return res
+
+
 def cfg5(afb, dev):
     out = []
     S, V, C = 256, 16, 8
