@@ -40,7 +40,8 @@ def reduce_view_grads(d_params: torch.Tensor, group=None) -> torch.Tensor:
     """``d_params[B_local, V, P]`` (per-sample gradients of the view parameters produced by the backward
     kernel) -> ``[V, P]`` summed over the local batch and all ranks: the single collective of the path.  With the peer-memory
     kernels enabled the local sum and the all-reduce are ONE kernel (``afb_peer_collective``), else ``sum`` + NCCL."""
-    if is_distributed() and _PEER is not None and group is None and d_params.dtype == torch.float32:
+    if is_distributed() and _PEER is not None and group is None and d_params.dtype == torch.float32 and \
+            d_params[0].numel() <= _PEER.n_max:
         return _PEER.all_reduce_sum(d_params.contiguous().view(d_params.shape[0], -1), PeerCollectives.CH_GRADS,
                                     pre_sum=d_params.shape[0]).view(d_params.shape[1:])
     g = d_params.sum(dim=0).contiguous()
@@ -108,14 +109,14 @@ class PeerCollectives:
     CH_PADS, CH_DPAD, CH_GRADS = 0, 1, 2
     N_CHANNELS = 4
 
-    def __init__(self, device, n_max: int = 4096):
+    def __init__(self, device, n_max: int = 1024):
         import ctypes as C
         import torch.distributed._symmetric_memory as symm
         from . import _lib as L
         self._L, self._C = L, C
         self.device = torch.device(device)
         self.rank, self.world, self.n_max = dist.get_rank(), dist.get_world_size(), int(n_max)
-        n_floats = int(L.lib().afb_peer_buffer_floats(self.N_CHANNELS, self.n_max))
+        n_floats = int(L.lib().afb_peer_buffer_floats(self.N_CHANNELS, self.n_max, self.world))
         self.buf = symm.empty(n_floats, dtype=torch.float32, device=self.device)
         self.buf.zero_()
         try:
@@ -162,7 +163,7 @@ class PeerCollectives:
             raise RuntimeError(f"afb_peer_collective: peer {int(self.err.item()) - 1} did not arrive within the spin bound")
 
 
-def enable_peer_collectives(device, n_max: int = 4096):
+def enable_peer_collectives(device, n_max: int = 1024):
     """Route exchange_pads / reduce_view_grads through the NVLink peer-memory kernels (call once per process after
     ``init_process_group``, on every rank).  Returns the :class:`PeerCollectives` (or raises if symmetric memory is unavailable)."""
     global _PEER

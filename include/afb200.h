@@ -288,15 +288,15 @@ int afb_label_extent_search(const void* labels, int dtype, int D, int H, int W, 
                             const float* dir_dev, double init_end, double* out_dev, void* stream);
 
 /* ---- the sharded path's collectives over NVLink peer memory -------------------------
- * One single-CTA kernel: copy the local contribution (optionally summed over `pre_sum` rows of `in`) into this rank's
- * symmetric buffer, publish the epoch to every peer, wait (bounded, ~2 s, then *err != 0) until every peer has published,
- * reduce the peers' slots in rank order.  op 0: out[n] = sum over ranks; op 1: out[world*n] = all-gather (rank-major);
+ * One single-CTA kernel: push the local contribution (optionally summed over `pre_sum` rows of `in`) into this rank's slot
+ * of EVERY rank's symmetric buffer, publish the epoch to every peer, wait (bounded, ~2 s, then *err != 0) until every peer has
+ * published, reduce the slots of the own buffer in rank order.  op 0: out[n] = sum over ranks; op 1: out[world*n] = all-gather (rank-major);
  * op 2: n/2 (min, multiplicity) pairs -> the pairs of the whole batch (minimum over ranks, multiplicities of its holders summed).
  * bufs_dev: DEVICE array of `world` pointers, entry r = this process' mapping of rank r's buffer of
- * afb_peer_buffer_floats(n_channels, n_max) floats (symmetric / peer-mapped memory, zeroed before the first call; the host -
+ * afb_peer_buffer_floats(n_channels, n_max, world) floats (symmetric / peer-mapped memory, zeroed before the first call; the host -
  * e.g. torch.distributed._symmetric_memory - allocates and exchanges the mappings).  epoch: device uint32[n_channels],
  * zeroed, private to the rank.  Independent exchanges use different channels.  Stream-ordered, CUDA-graph capturable. */
-int64_t afb_peer_buffer_floats(int n_channels, int n_max);
+int64_t afb_peer_buffer_floats(int n_channels, int n_max, int world);
 int afb_peer_collective(void* const* bufs_dev, int rank, int world, int op, int channel, int n_channels, int n, int n_max,
                         int pre_sum, const float* in, float* out, void* epoch, int* err, void* stream);
 
