@@ -172,8 +172,12 @@ embed_slab_kernel(const float* __restrict__ x, const EmbedView* __restrict__ vie
     const float ta = t[axis];
     const float g0 = t[0] * (a1 * w + a0) + t[1] * (a1 * h + a0) + t[2] * (a1 * d + a0) + t[3];
     const float ix0 = ((g0 + 1.0f) * Sf - 1.0f) * 0.5f;
-    const float pc = (mid - ix0) / ta, half = 1.05f / fabsf(ta);
-    const int plo = (int)ceilf(pc - half);
+    // |ta| ~ 0 on the steepest axis means ix is (numerically) constant over the whole volume - a degenerate / strongly
+    // anisotropic inverse affine: every voxel of the line is a candidate or none is (no division by ~0)
+    const bool flat = fabsf(ta) < 1e-6f;
+    if (flat && fabsf(ix0 - mid) >= 1.05f) return;
+    const float pc = flat ? 0.0f : (mid - ix0) / ta, half = flat ? 3.0e38f : 1.05f / fabsf(ta);
+    const int plo = flat ? 0 : (int)ceilf(pc - half);
     const size_t S2 = (size_t)S * S, S3 = S2 * S;
     const float* __restrict__ xs = x + ((size_t)b * V + v) * c * S2;
     for (int k = k0; k < K; k += Kgrid) {
