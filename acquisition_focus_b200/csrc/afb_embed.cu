@@ -153,8 +153,11 @@ embed_zero_kernel(float4* __restrict__ out4, size_t n4, float* __restrict__ out,
 // (channel loop unrolled so that the 4-tap gathers of several channels are in flight together).
 __global__ void __launch_bounds__(ETHREADS)
 embed_slab_kernel(const float* __restrict__ x, const EmbedView* __restrict__ views, int B, int V, int c, int S,
-                  int Kgrid, AxisConst ax, float* __restrict__ out) {
+                  int Kgrid, AxisConst ax, float* __restrict__ out, int ch_per_cta) {
     const int bv = blockIdx.y, b = bv / V, v = bv % V;
+    // blockIdx.z: channel chunk.  The kernel is latency bound (a tap computation, then gathers channel after channel), so the
+    // channels of a candidate voxel are spread over several CTAs: more loads in flight, a shorter chain per thread
+    const int ch0 = blockIdx.z * ch_per_cta, ch1 = min(c, ch0 + ch_per_cta);
     float t[12];
 #pragma unroll
     for (int q = 0; q < 12; ++q) t[q] = __ldg(views[bv].t + q);
@@ -188,7 +191,7 @@ embed_slab_kernel(const float* __restrict__ x, const EmbedView* __restrict__ vie
         if (tp.inb == 0u) continue;
         float* __restrict__ o = out + ((size_t)b * V + v) * c * S3 + ((size_t)d * S + h) * S + w;
 #pragma unroll 4
-        for (int ch = 0; ch < c; ++ch) {
+        for (int ch = ch0; ch < ch1; ++ch) {
             const float* __restrict__ xc = xs + (size_t)ch * S2;
             float acc = 0.0f;
 #pragma unroll
@@ -621,8 +624,12 @@ extern "C" int afb_embed_fwd(const float* x, const float* affines, int B, int V,
     // |t_axis| >= 0.58 for a rotation => K <= 5 slab voxels per line; views that need more loop inside the kernel
     if ((long long)S * S * 8 >= 2147483647ll) return AFB_ESHAPE;
     const int Kgrid = S < 6 ? S : 6;
-    dim3 grid((unsigned)(((long long)S * S * Kgrid + ETHREADS - 1) / ETHREADS), B * V);
-    embed_slab_kernel<<<grid, ETHREADS, 0, st>>>(x, views, B, V, c, S, Kgrid, ax, out);
+    const char* es = getenv("AFB_EMBED_SLAB_CH");          // A/B knob (profiles/ab_embed_roles.py): channels per slab CTA
+    int chp = es ? atoi(es) : 4;
+    if (chp < 1) chp = 1;
+    if ((c + chp - 1) / chp > 65535) chp = (c + 65534) / 65535;
+    dim3 grid((unsigned)(((long long)S * S * Kgrid + ETHREADS - 1) / ETHREADS), B * V, (unsigned)((c + chp - 1) / chp));
+    embed_slab_kernel<<<grid, ETHREADS, 0, st>>>(x, views, B, V, c, S, Kgrid, ax, out, chp);
     return (int)cudaGetLastError();
 }
 
