@@ -155,8 +155,9 @@ __global__ void __launch_bounds__(ETHREADS)
 embed_slab_kernel(const float* __restrict__ x, const EmbedView* __restrict__ views, int B, int V, int c, int S,
                   int Kgrid, AxisConst ax, float* __restrict__ out, int ch_per_cta) {
     const int bv = blockIdx.y, b = bv / V, v = bv % V;
-    // blockIdx.z: channel chunk.  The kernel is latency bound (a tap computation, then gathers channel after channel), so the
-    // channels of a candidate voxel are spread over several CTAs: more loads in flight, a shorter chain per thread
+    // blockIdx.z: channel chunk.  Measured on the B200 (stage 0, profiles/r2_ab_embed_slab.json): spreading the channels of a
+    // candidate voxel over CTAs LOSES (1 / 4 / 16 channels per CTA: 0.58 / 0.42 / 0.39 ms for zero + slab) - the exact tap
+    // computation per candidate dominates, not the gather chain - so the host passes all channels (one chunk)
     const int ch0 = blockIdx.z * ch_per_cta, ch1 = min(c, ch0 + ch_per_cta);
     float t[12];
 #pragma unroll
@@ -625,7 +626,7 @@ extern "C" int afb_embed_fwd(const float* x, const float* affines, int B, int V,
     if ((long long)S * S * 8 >= 2147483647ll) return AFB_ESHAPE;
     const int Kgrid = S < 6 ? S : 6;
     const char* es = getenv("AFB_EMBED_SLAB_CH");          // A/B knob (profiles/ab_embed_roles.py): channels per slab CTA
-    int chp = es ? atoi(es) : 4;
+    int chp = es ? atoi(es) : c;
     if (chp < 1) chp = 1;
     if ((c + chp - 1) / chp > 65535) chp = (c + 65534) / 65535;
     dim3 grid((unsigned)(((long long)S * S * Kgrid + ETHREADS - 1) / ETHREADS), B * V, (unsigned)((c + chp - 1) / chp));
