@@ -630,6 +630,7 @@ extern "C" int afb_embed_fwd(const float* x, const float* affines, int B, int V,
     if (chp < 1) chp = 1;
     if ((c + chp - 1) / chp > 65535) chp = (c + 65534) / 65535;
     dim3 grid((unsigned)(((long long)S * S * Kgrid + ETHREADS - 1) / ETHREADS), B * V, (unsigned)((c + chp - 1) / chp));
+    // (a register budget for 3 or 4 resident CTAs per SM instead of 2 changes nothing: 0.412 / 0.421 / 0.404 ms at stage 0)
     embed_slab_kernel<<<grid, ETHREADS, 0, st>>>(x, views, B, V, c, S, Kgrid, ax, out, chp);
     return (int)cudaGetLastError();
 }
