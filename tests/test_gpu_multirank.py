@@ -74,8 +74,17 @@ def _worker(rank, world, port, q):
             g3 = par.reduce_view_grads(p3[5])
             for _ in range(3):                                    # epochs / slot parity over repeated calls
                 g3b = par.reduce_view_grads(p3[5])
+            # the three ops of afb_peer_collective against NCCL on arbitrary data
+            x = torch.arange(37, dtype=torch.float32, device="cuda") * (rank + 1.5)
+            want = x.clone(); dist.all_reduce(want)
+            got = pc.all_reduce_sum(torch.stack([x * 0.25, x * 0.75]), 3, pre_sum=2)                     # local rows summed first
+            gath = torch.empty(world * 37, device="cuda"); dist.all_gather_into_tensor(gath, x)
+            ops_ok = torch.allclose(got, want, rtol=1e-6) and torch.equal(pc.all_gather(x, 3), gath)
+            rows = torch.tensor([[1.0 + rank, 3.0], [-2.0, 5.0 + rank]], device="cuda")
+            merged = pc.merge_pads(rows)
+            ops_ok = ops_ok and merged.tolist() == [[1.0, 3.0], [-2.0, 11.0]]
             pc.check()
-            peer_ok = bool(all(torch.equal(a, b) for a, b in zip(p3[:4], (ys, yl, yi, ga)))
+            peer_ok = bool(ops_ok and all(torch.equal(a, b) for a, b in zip(p3[:4], (ys, yl, yi, ga)))
                            and (p3[4] - dsoft).abs().max().item() <= 1e-6 * dsoft.abs().max().item()
                            and (g3 - g).abs().max().item() <= 1e-6 * g.abs().max().item() and torch.equal(g3, g3b)
                            and all(torch.equal(a, b) for a, b in zip(p3[6], pads)))

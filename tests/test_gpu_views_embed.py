@@ -325,3 +325,25 @@ def test_fused_three_way_forward_bitwise(afb, S):
     o2 = afb.acquire_views(soft, None, case["image"].cuda(), case["nii"].cuda(), gpre, params, INIT.repeat(V, 1).cuda(), fused_forward=True, **kw)
     assert torch.equal(o1[0], a[0]) and torch.equal(o1[1], a[1]) and o1[2] is None
     assert torch.equal(o2[0], a[0]) and torch.equal(o2[2], a[2]) and o2[1] is None
+
+
+@pytest.mark.parametrize("C,label_dtype", [(16, torch.uint8), (4, torch.int32), (8, torch.int16), (8, torch.int64)])
+def test_fused_three_way_forward_other_layouts(afb, C, label_dtype):
+    """afb_slice_fwd3 with other channel counts / label storage types (16-byte channel vectors: 16 x u8, 8 x i16, 4 x i32,
+    2 x i64) and a 2-channel image, against the per-volume launches (bitwise)."""
+    S, B, V = 32, 2, 2
+    gen = torch.Generator().manual_seed(5)
+    lab = torch.randint(0, C, (B, S, S, S), generator=gen)
+    onehot = torch.nn.functional.one_hot(lab, C).permute(0, 4, 1, 2, 3)
+    soft = (onehot.float() + 0.25 * torch.rand(onehot.shape, generator=gen).permute(0, 1, 2, 3, 4)).cuda()      # channels-last view
+    label = onehot.to(label_dtype).cuda()
+    image = torch.randn(B, 2, S, S, S, generator=gen).cuda()
+    case = cases.atm_case(S, B, V, seed=59)
+    gpre = torch.stack(case["gpre"], dim=1).cuda()
+    params = torch.stack(case["params"], dim=1).cuda()
+    kw = dict(offset_clip=0.2, zoom_clip=0.0, spat=S, slice_fov_mm=case["slice_fov_mm"].tolist(), slice_fov_vox=case["slice_fov_vox"].tolist())
+    a = afb.acquire_views(soft, label, image, case["nii"].cuda(), gpre, params, INIT.repeat(V, 1).cuda(), fused_forward=False, **kw)
+    b = afb.acquire_views(soft, label, image, case["nii"].cuda(), gpre, params, INIT.repeat(V, 1).cuda(), fused_forward=True, **kw)
+    assert b[1].dtype == label_dtype and b[2].shape == (B, V, 2, S, S, 1)
+    for x, y in zip(a, b):
+        assert x.dtype == y.dtype and torch.equal(x, y)
