@@ -675,7 +675,10 @@ extern "C" int afb_slice_fwd3(const afb_volume* soft, const afb_volume* label, c
         if (label->B != soft->B || label->D != soft->D || label->H != soft->H || label->W != soft->W) return AFB_ESHAPE;
         const int eb = label->dtype == AFB_I64 ? 8 : label->dtype == AFB_I32 ? 4 : label->dtype == AFB_I16 ? 2 : label->dtype == AFB_U8 ? 1 : 0;
         if (!eb) return AFB_EDTYPE;
-        if (channels_last_vec(label, eb, nullptr, 16) != 16) return AFB_EUNSUPPORTED;
+        const int nl = 16 / eb;            // elements per 16-byte channel vector (up to 16 for u8: own check, not channels_last_vec)
+        if (label->sC != 1 || label->C % nl || ((uintptr_t)label->data % 16) || label->sW % nl || label->sH % nl || label->sD % nl ||
+            label->sB % nl)
+            return AFB_EUNSUPPORTED;
     }
     if (image) {
         if (!y_image) return AFB_EINVAL;
