@@ -107,3 +107,71 @@ def default_nifti_affine(batch: int, spacing_mm: float = 1.5) -> torch.Tensor:
     a = torch.eye(4, dtype=torch.float64) * spacing_mm
     a[3, 3] = 1.0
     return a[None].repeat(batch, 1, 1)
+
+# ------------------------------------------------------------------------------------------------
+# deterministic case builders (inputs of tests, smoke and the bench variants): closed forms / seeded PCG64 streams
+# ------------------------------------------------------------------------------------------------
+def pattern(shape, k: float = 1.0) -> torch.Tensor:
+    """Deterministic pseudo-random upstream gradient in [-1,1] (closed form)."""
+    n = int(np.prod(shape))
+    v = np.cos(np.arange(n, dtype=np.float64) * 0.6180339887498949 * k + 0.3)
+    return torch.from_numpy(v.astype(np.float32).reshape(shape))
+
+
+def randn(shape, seed: int) -> torch.Tensor:
+    return torch.from_numpy(np.random.default_rng(seed).standard_normal(shape, dtype=np.float32))
+
+
+def randint(lo, hi, shape, seed: int) -> torch.Tensor:
+    return torch.from_numpy(np.random.default_rng(seed).integers(lo, hi, size=shape, dtype=np.int64))
+
+
+def phantom_batch(S: int, B: int, num_classes: int = 8):
+    """B label maps [B,S,S,S] int64: the phantom and axis-permuted/flipped variants."""
+    base = heart_phantom(S)
+    variants = [base, np.ascontiguousarray(base.transpose(1, 0, 2)[::-1]),
+                np.ascontiguousarray(base[:, ::-1, :]), np.ascontiguousarray(base.transpose(2, 1, 0))]
+    lab = np.stack([variants[b % len(variants)] for b in range(B)])
+    return torch.from_numpy(lab)
+
+
+def one_hot_volumes(lab: torch.Tensor, num_classes: int = 8):
+    """As running/run_dl.py:261-264: ``rearrange(one_hot(label), 'B D H W OH -> B OH D H W')``
+    (a channels-last *view*) and its ``.float()``."""
+    oh = torch.nn.functional.one_hot(lab, num_classes).permute(0, 4, 1, 2, 3)
+    return oh, oh.float()
+
+
+def atm_case(S: int, B: int, V: int, seed: int, zoom_clip: float = 0.0, offset_clip: float = 0.2,
+             num_classes: int = 8):
+    """cfg-2 style inputs: per view a p2CH pre-affine with per-sample augmentation,
+    MLP-head outputs (R6 | offset logits | zoom logit)."""
+    gen = torch.Generator().manual_seed(seed)
+    views = phantom_view_affines()
+    R = int(round(offset_clip * S))
+    lab = phantom_batch(S, B, num_classes)
+    label_oh, soft = one_hot_volumes(lab, num_classes)
+    img = torch.stack([torch.from_numpy(phantom_image(lab[b].numpy(), seed=seed + b)) for b in range(B)])[:, None]
+    nii = default_nifti_affine(B, 192.0 / S)
+    gpre, params = [], []
+    for v in range(V):
+        aug = torch.stack([random_aug_affine(gen, 0.1, 0.2, 0.0) for _ in range(B)])
+        gpre.append(views["p2CH"][None].repeat(B, 1, 1) @ aug)
+        r6 = torch.tensor([1.0, 0, 0, 0, 1.0, 0]) + 0.3 * torch.randn(B, 6, generator=gen)
+        params.append(torch.cat([r6, torch.randn(B, 3 * R, generator=gen), torch.randn(B, 1, generator=gen)], dim=1))
+    return dict(S=S, B=B, V=V, R=R, lab=lab, label=label_oh, soft=soft, image=img, nii=nii,
+                gpre=gpre, params=params, zoom_clip=zoom_clip, offset_clip=offset_clip,
+                slice_fov_mm=torch.tensor([192.0, 192.0, 192.0 / S]), slice_fov_vox=torch.tensor([S, S, 1]),
+                volume_fov_mm=torch.tensor([192.0, 192.0, 192.0]), volume_fov_vox=torch.tensor([S, S, S]))
+
+
+def embed_case(S: int, c: int, V: int, B: int, seed: int):
+    gen = torch.Generator().manual_seed(seed)
+    x = randn((B, V * c, S, S), seed)
+    views = phantom_view_affines()
+    names = ["p2CH", "p4CH", "SA-1", "4CH", "2CH", "axial"]
+    gas = []
+    for v in range(V):
+        aug = torch.stack([random_aug_affine(gen, 0.3, 0.3, 0.05) for _ in range(B)])
+        gas.append(views[names[v % len(names)]][None].repeat(B, 1, 1) @ aug)
+    return dict(S=S, c=c, V=V, B=B, x=x, affines=gas)

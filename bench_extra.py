@@ -9,6 +9,9 @@
 Each line: {"config": ..., "ms": ..., "value": ..., "unit": ..., "bytes": algorithmic bytes, "gbs": ...,
             "torch_cuda_ms": same op through ATen's sm_100 kernels on the same GPU (the Blackwell bar)}.
 CUDA events, 3 warm-ups, mean of 10.  Run on the GPU box: python bench_extra.py > profiles/...json
+
+Inputs come from the product's own synthetic module.  `oracle.af_oracle` is imported ONLY inside the `ref()` / ATen-CUDA
+baseline legs (the reference's op sequence timed on the GPU as the Blackwell bar) - never on a measured product path.
 """
 from __future__ import annotations
 
@@ -69,7 +72,7 @@ def cfg1(afb, dev):
 
 
 def cfg2(afb, dev):
-    from oracle import cases
+    from acquisition_focus_b200 import synthetic as cases          # input builders (product-side synthetic module)
     case = cases.atm_case(128, 2, 3, seed=43)
     soft = case["soft"].to(dev).requires_grad_(True)
     label, image, nii = case["label"].to(dev), case["image"].to(dev), case["nii"].to(dev)
@@ -113,7 +116,7 @@ def cfg2(afb, dev):
 
 
 def cfg3(afb, dev):
-    from oracle import cases
+    from acquisition_focus_b200 import synthetic as cases          # input builders (product-side synthetic module)
     out = []
     for B in (1, 2):
         tot_f = tot_b = tot_rf = tot_rb = 0.0
@@ -159,7 +162,7 @@ def cfg3_summary(afb, dev, B=2, V=6):
     """cfg3 for the driver-run bench line: all six U-Net stages at B=2, V=6, forward and forward+backward, per stage and summed,
     with the HBM roofline fraction of each stage's forward (compulsory bytes: the [B,V*c,S^3] output written once + the feature
     maps read once) and the same op through ATen's sm_100 kernels (oracle op sequence on the GPU), stage 0 and summed."""
-    from oracle import cases
+    from acquisition_focus_b200 import synthetic as cases          # input builders (product-side synthetic module)
     import json as _json
     peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
     hbm = float(_json.load(open(peaks))["hbm_gbs"]) if os.path.exists(peaks) else 6650.0
@@ -230,7 +233,7 @@ def f1_resample_3d(afb, dev, B=8, V=3):
     input read once.  Three routes: channels-last soft volume (what run_dl.py:261-264 hands over), planar soft volume (generic
     kernel vs one transposing copy + channels-last kernel), and straight from the uint8 label map (no one-hot input at all)."""
     import json as _json
-    from oracle import cases
+    from acquisition_focus_b200 import synthetic as cases          # input builders (product-side synthetic module)
     from oracle import af_oracle as O
     from acquisition_focus_b200 import functional as AF
     peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")

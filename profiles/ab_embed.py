@@ -10,7 +10,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 import bench  # noqa: E402
 import acquisition_focus_b200 as afb  # noqa: E402
-from oracle import cases  # noqa: E402   (input builder only)
+from acquisition_focus_b200 import synthetic as cases  # noqa: E402
 
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)

@@ -7,7 +7,7 @@ sys.path.insert(0, ROOT)
 import torch
 import bench
 import acquisition_focus_b200 as afb
-from oracle import cases
+from acquisition_focus_b200 import synthetic as cases
 
 dev = torch.device("cuda", 0)
 B, V, c, S = 2, 6, 16, 128

@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT)
 import torch
 import bench
 import acquisition_focus_b200 as afb
-from oracle import cases
+from acquisition_focus_b200 import synthetic as cases
 dev = torch.device("cuda", 0)
 res = {}
 for (c, S) in ((16, 128), (32, 64), (64, 32)):

@@ -16,7 +16,7 @@ import sys
 sys.path.insert(0, ".")
 import torch
 import acquisition_focus_b200 as afb
-from oracle import cases
+from acquisition_focus_b200 import synthetic as cases
 dev = torch.device("cuda", 0)
 B, V = 2, 6
 case0 = cases.embed_case(128, 16, V, B, seed=300)
