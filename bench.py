@@ -598,7 +598,7 @@ def run_ours(args):
     clk = clocks.stop() if rank == 0 else None
     value = total * V / (ms_per_step / 1e3)
     if mode != "eager":
-        for _ in range(2):               # the first eager step after a capture re-allocates from the regular pool (cudaMalloc)
+        for _ in range(12):              # the eager steps after a capture re-populate the regular pool (a few cudaMallocs of GBs)
             wl.step()
         ms_eager = time_steps(wl.step, min(args.steps, 10), dev, world, sync_all)
     else:
