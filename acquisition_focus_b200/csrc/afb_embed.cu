@@ -237,128 +237,6 @@ __device__ inline void embed_chain(const EmbedView& ev, const double* __restrict
     for (int r = 0; r < 4; ++r) d_ga[r * 4 + 3] = (float)dA[r * 4 + 3];
 }
 
-// grid = (pixel tiles, channel chunks, B*V); one thread = one feature-map pixel (r,q) x <=ECH channels
-__global__ void __launch_bounds__(ETHREADS)
-embed_bwd_kernel(const float* __restrict__ go, const float* __restrict__ x, const EmbedView* __restrict__ views,
-                 int B, int V, int c, int S, AxisConst ax, float* __restrict__ d_x, float* __restrict__ d_aff,
-                 double* __restrict__ ws_acc, unsigned* __restrict__ ws_counter) {
-    __shared__ EmbedView ev;
-    __shared__ float base[256];
-    __shared__ float red[ETHREADS / 32][12];
-    __shared__ double dT[12];
-    __shared__ bool is_last;
-    const int bv = blockIdx.z, b = bv / V, v = bv % V;
-    {
-        const unsigned* __restrict__ src = reinterpret_cast<const unsigned*>(views + bv);
-        unsigned* dst = reinterpret_cast<unsigned*>(&ev);
-        for (int i = threadIdx.x; i < (int)(sizeof(EmbedView) / 4); i += ETHREADS) dst[i] = __ldg(src + i);
-    }
-    const bool use_tab = S <= 256;
-    if (use_tab) for (int i = threadIdx.x; i < S; i += ETHREADS) base[i] = base_coord(i, ax);
-    __syncthreads();
-    float part[12];
-#pragma unroll
-    for (int q = 0; q < 12; ++q) part[q] = 0.0f;
-
-    const int pix = blockIdx.x * ETHREADS + threadIdx.x;
-    const int c0 = blockIdx.y * ECH;
-    const int nch = min(ECH, c - c0);
-    const size_t S2 = (size_t)S * S, S3 = S2 * S;
-    if (pix < S * S) {
-        const int r = pix / S, q = pix % S;                     // r: row (D index), q: column (H index)
-        const int mid = S >> 1;
-        const float Sf = (float)S;
-        // centre of the pixel's influence box in volume index space: A * normalised(mid, q, r)
-        const float pn[3] = {(2.0f * mid + 1.0f) / Sf - 1.0f, (2.0f * q + 1.0f) / Sf - 1.0f, (2.0f * r + 1.0f) / Sf - 1.0f};
-        int lo[3], hi[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const float g = ev.fwd[k * 4 + 0] * pn[0] + ev.fwd[k * 4 + 1] * pn[1] + ev.fwd[k * 4 + 2] * pn[2] + ev.fwd[k * 4 + 3];
-            const float vc = ((g + 1.0f) * Sf - 1.0f) * 0.5f;
-            const float ext = fabsf(ev.fwd[k * 4 + 0]) + fabsf(ev.fwd[k * 4 + 1]) + fabsf(ev.fwd[k * 4 + 2]) + 0.05f;
-            lo[k] = max(0, (int)ceilf(vc - ext));
-            hi[k] = min(S - 1, (int)floorf(vc + ext));
-        }
-        const float* __restrict__ gbase = go + (((size_t)b * V + v) * c + c0) * S3;
-        const float* __restrict__ xp = x + (((size_t)b * V + v) * c + c0) * S2 + pix;
-        float acc[ECH], xv[ECH];
-#pragma unroll
-        for (int ch = 0; ch < ECH; ++ch) { acc[ch] = 0.0f; xv[ch] = (d_aff && ch < nch) ? __ldg(xp + (size_t)ch * S2) : 0.0f; }
-        // (lo/hi index order: k = 0 -> w (x), 1 -> h (y), 2 -> d (z))
-        for (int d = lo[2]; d <= hi[2]; ++d) {
-            const float bz = use_tab ? base[d] : base_coord(d, ax);
-            for (int h = lo[1]; h <= hi[1]; ++h) {
-                const float by = use_tab ? base[h] : base_coord(h, ax);
-                for (int w = lo[0]; w <= hi[0]; ++w) {
-                    const float bx = use_tab ? base[w] : base_coord(w, ax);
-                    const Tap tp = taps_of(ev.t, bx, by, bz, S);
-                    if (tp.inb == 0u) continue;
-                    int t = -1;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (((tp.inb >> k) & 1u) && tp.off[k] == pix) t = k;
-                    if (t < 0) continue;
-                    const float wt = tp.w[t];
-                    const float* __restrict__ gp = gbase + ((size_t)d * S + h) * S + w;
-                    float s = 0.0f;
-#pragma unroll
-                    for (int ch = 0; ch < ECH; ++ch) {
-                        if (ch < nch) {
-                            const float gv = __ldg(gp + (size_t)ch * S3);
-                            acc[ch] = fmaf(wt, gv, acc[ch]);
-                            s = fmaf(gv, xv[ch], s);
-                        }
-                    }
-                    if (d_aff) {
-                        const int dy = t & 1, dz = t >> 1;
-                        const float hs = 0.5f * Sf;
-                        const float ggx = tp.sx * s * tp.wy[dy] * tp.wz[dz] * hs;
-                        const float ggy = (dy ? s : -s) * tp.wx * tp.wz[dz] * hs;
-                        const float ggz = (dz ? s : -s) * tp.wx * tp.wy[dy] * hs;
-                        part[0] += ggx * bx; part[1] += ggx * by; part[2] += ggx * bz; part[3] += ggx;
-                        part[4] += ggy * bx; part[5] += ggy * by; part[6] += ggy * bz; part[7] += ggy;
-                        part[8] += ggz * bx; part[9] += ggz * by; part[10] += ggz * bz; part[11] += ggz;
-                    }
-                }
-            }
-        }
-        if (d_x) {
-            float* __restrict__ dxp = d_x + (((size_t)b * V + v) * c + c0) * S2 + pix;
-#pragma unroll
-            for (int ch = 0; ch < ECH; ++ch)
-                if (ch < nch) dxp[(size_t)ch * S2] = acc[ch];
-        }
-    }
-    if (!d_aff) return;
-    const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-    for (int q = 0; q < 12; ++q) {
-        const float rr = warp_sum(part[q]);
-        if (lane == 0) red[wi][q] = rr;
-    }
-    __syncthreads();
-    if (threadIdx.x < 12) {
-        double t = 0.0;
-#pragma unroll
-        for (int ww = 0; ww < ETHREADS / 32; ++ww) t += (double)red[ww][threadIdx.x];
-        if (t != 0.0) atomicAdd(ws_acc + (size_t)bv * 16 + threadIdx.x, t);
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = atomicAdd(ws_counter + bv, 1u) == gridDim.x * gridDim.y - 1;
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    if (threadIdx.x < 12) {
-        dT[threadIdx.x] = __ldcg(ws_acc + (size_t)bv * 16 + threadIdx.x);
-        ws_acc[(size_t)bv * 16 + threadIdx.x] = 0.0;
-    }
-    if (threadIdx.x == 0) ws_counter[bv] = 0u;
-    __syncthreads();
-    if (threadIdx.x == 0) embed_chain(ev, dT, d_aff + ((size_t)v * B + b) * 16);
-}
-
-
 // ================================================================================================
 // Batched, single-pass forward/backward over ALL stages of one U-Net pass (HybridUnet.forward embeds the six encoder skips
 // with the same affines, models/hybrid_unet.py:40-43).
@@ -467,7 +345,7 @@ embed_fwd_fused_kernel(const __grid_constant__ EmbedBatch eb, const EmbedView* _
     }
 }
 
-// backward, all stages in one launch: the gather kernel above (embed_bwd_kernel's body) per (stage, pixel tile, channel chunk,
+// backward, all stages in one launch: GATHER over the 2-D feature-map pixels per (stage, pixel tile, channel chunk,
 // b*V + v); the 12 sums of d(theta) are accumulated over ALL stages (the chain through inverse() and the column normalisation
 // is linear in them) and chained once by the last CTA of each (b,v).
 __global__ void __launch_bounds__(ETHREADS)
@@ -521,20 +399,58 @@ embed_bwd_fused_kernel(const __grid_constant__ EmbedBatch eb, const EmbedView* _
         float acc[ECH], xv[ECH];
 #pragma unroll
         for (int ch = 0; ch < ECH; ++ch) { acc[ch] = 0.0f; xv[ch] = (d_aff && ch < nch) ? __ldg(xp + (size_t)ch * S2) : 0.0f; }
+        // Along a line (d,h) the three source coordinates are affine in w with slopes t[0], t[4], t[8] (index units), so the
+        // voxels that can sample this pixel - ix in [mid-1, mid+1), iy in (q-1, q+1), iz in (r-1, r+1) - form ONE interval of w:
+        // solved in closed form (0.05-voxel margin), only its few members run the exact tap code.  (The first version tested
+        // every voxel of the bounding box.)  Per line: three fma pairs; the reciprocal slopes are per-thread constants.
+        const float cen[3] = {(float)mid, (float)q, (float)r};
+        float c000[3], inv[3];                 // coordinate k (index units) of voxel (0,0,0), relative to the pixel; 1/slope or 0 (flat)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float* __restrict__ tk = ev.t + 4 * k;
+            const float a0 = 1.0f / Sf - 1.0f;
+            const float g0 = (tk[0] + tk[1] + tk[2]) * a0 + tk[3];
+            c000[k] = ((g0 + 1.0f) * Sf - 1.0f) * 0.5f - cen[k];
+            inv[k] = fabsf(tk[0]) * Sf < 0.02f ? 0.0f : 1.0f / tk[0];
+        }
         for (int d = lo[2]; d <= hi[2]; ++d) {
             const float bz = use_tab ? base[d] : base_coord(d, ax);
             for (int h = lo[1]; h <= hi[1]; ++h) {
                 const float by = use_tab ? base[h] : base_coord(h, ax);
-                for (int w = lo[0]; w <= hi[0]; ++w) {
-                    const float bx = use_tab ? base[w] : base_coord(w, ax);
-                    const Tap tp = taps_of(ev.t, bx, by, bz, S);
-                    if (tp.inb == 0u) continue;
-                    int tt = -1;
+                float wlo = (float)lo[0], whi = (float)hi[0];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (((tp.inb >> k) & 1u) && tp.off[k] == pix) tt = k;
-                    if (tt < 0) continue;
-                    const float wt = tp.w[tt];
+                for (int k = 0; k < 3; ++k) {
+                    const float rel = fmaf(ev.t[4 * k + 1], (float)h, fmaf(ev.t[4 * k + 2], (float)d, c000[k]));   // at w = 0
+                    if (inv[k] == 0.0f) {
+                        if (fabsf(rel) > 1.07f) { wlo = 1.0f; whi = 0.0f; }               // constant along the line and out of reach
+                    } else {
+                        const float u = (-1.05f - rel) * inv[k], v2 = (1.05f - rel) * inv[k];
+                        wlo = fmaxf(wlo, fminf(u, v2));
+                        whi = fminf(whi, fmaxf(u, v2));
+                    }
+                }
+                const int w0 = (int)ceilf(wlo), w1 = (int)floorf(whi);
+                for (int w = w0; w <= w1; ++w) {
+                    const float bx = use_tab ? base[w] : base_coord(w, ax);
+                    // does voxel (w,h,d) sample pixel (q,r)?  Same arithmetic as taps_of (the forward's), reduced to the one
+                    // tap (dy,dz) = (q - floor(iy), r - floor(iz)) that can hit this pixel.
+                    const float ix = unnormalize(grid_coord(ev.t + 0, bx, by, bz), Sf);
+                    const float x0f = floorf(ix);
+                    const int x0 = (int)x0f;
+                    if (x0 != mid && x0 + 1 != mid) continue;
+                    const float iy = unnormalize(grid_coord(ev.t + 4, bx, by, bz), Sf);
+                    const float y0f = floorf(iy);
+                    const int dy = q - (int)y0f;
+                    if ((unsigned)dy > 1u) continue;
+                    const float iz = unnormalize(grid_coord(ev.t + 8, bx, by, bz), Sf);
+                    const float z0f = floorf(iz);
+                    const int dz = r - (int)z0f;
+                    if ((unsigned)dz > 1u) continue;
+                    const float wx = x0 == mid ? __fsub_rn(__fadd_rn(x0f, 1.0f), ix) : __fsub_rn(ix, x0f);
+                    const float sx = x0 == mid ? -1.0f : 1.0f;
+                    const float wy = dy ? __fsub_rn(iy, y0f) : __fsub_rn(__fadd_rn(y0f, 1.0f), iy);
+                    const float wz = dz ? __fsub_rn(iz, z0f) : __fsub_rn(__fadd_rn(z0f, 1.0f), iz);
+                    const float wt = __fmul_rn(__fmul_rn(wx, wy), wz);
                     const float* __restrict__ gp = gbase + ((size_t)d * S + h) * S + w;
                     float ssum = 0.0f;
 #pragma unroll
@@ -546,11 +462,10 @@ embed_bwd_fused_kernel(const __grid_constant__ EmbedBatch eb, const EmbedView* _
                         }
                     }
                     if (d_aff) {
-                        const int dy = tt & 1, dz = tt >> 1;
                         const float hs = 0.5f * Sf;
-                        const float ggx = tp.sx * ssum * tp.wy[dy] * tp.wz[dz] * hs;
-                        const float ggy = (dy ? ssum : -ssum) * tp.wx * tp.wz[dz] * hs;
-                        const float ggz = (dz ? ssum : -ssum) * tp.wx * tp.wy[dy] * hs;
+                        const float ggx = sx * ssum * wy * wz * hs;
+                        const float ggy = (dy ? ssum : -ssum) * wx * wz * hs;
+                        const float ggz = (dz ? ssum : -ssum) * wx * wy * hs;
                         part[0] += ggx * bx; part[1] += ggx * by; part[2] += ggx * bz; part[3] += ggx;
                         part[4] += ggy * bx; part[5] += ggy * by; part[6] += ggy * bz; part[7] += ggy;
                         part[8] += ggz * bx; part[9] += ggz * by; part[10] += ggz * bz; part[11] += ggz;
@@ -635,22 +550,18 @@ extern "C" int afb_embed_fwd(const float* x, const float* affines, int B, int V,
     return (int)cudaGetLastError();
 }
 
+extern "C" int afb_embed_multi_bwd(int n_stages, const float* const* grad_out, const float* const* x, const int* c, const int* S,
+                                   float* const* d_x, const float* affines, int B, int V, float* d_affines, void* workspace,
+                                   void* stream);
+
 extern "C" int afb_embed_bwd(const float* grad_out, const float* x, const float* affines, int B, int V, int c, int S,
                              float* d_x, float* d_affines, void* workspace, void* stream) {
     if (!grad_out || !x || !affines || !workspace) return AFB_EINVAL;
     if (!d_x && !d_affines) return AFB_EINVAL;
-    if (B <= 0 || V <= 0 || c <= 0 || S <= 0 || (long long)B * V > 65535) return AFB_ESHAPE;
-    const int chunks = (c + ECH - 1) / ECH;
-    if (chunks > 65535) return AFB_ESHAPE;
-    const AxisConst ax = make_axis(S);
-    cudaStream_t st = (cudaStream_t)stream;
-    double* acc = (double*)workspace;
-    unsigned* counter = (unsigned*)(acc + (size_t)B * V * 16);
-    EmbedView* views = views_of(workspace, B * V);
-    embed_prologue_kernel<<<(B * V + 31) / 32, 32, 0, st>>>(affines, B, V, views);
-    dim3 grid((unsigned)((S * S + ETHREADS - 1) / ETHREADS), chunks, B * V);
-    embed_bwd_kernel<<<grid, ETHREADS, 0, st>>>(grad_out, x, views, B, V, c, S, ax, d_x, d_affines, acc, counter);
-    return (int)cudaGetLastError();
+    const float* go1[1] = {grad_out};
+    const float* x1[1] = {x};
+    float* dx1[1] = {d_x};
+    return afb_embed_multi_bwd(1, go1, x1, &c, &S, d_x ? dx1 : nullptr, affines, B, V, d_affines, workspace, stream);
 }
 
 

@@ -54,6 +54,28 @@ def fb_all():
     outs = afb.embed_slices_multi(xs, torch.stack(gas, 0), V)
     torch.autograd.backward(outs, gos)
 res["ms"]["all stages fwd+bwd, ONE launch each (afb_embed_multi_fwd/bwd)"] = bench._time(fb_all, dev)
+
+
+def bwd_only(idx):
+    """backward of the stages in idx alone (events around autograd.backward; the forward runs outside the timed region)"""
+    ts = []
+    for it in range(13):
+        for x in xs:
+            x.grad = None
+        for a in gas:
+            a.grad = None
+        outs = afb.embed_slices_multi([xs[i] for i in idx], torch.stack(gas, 0), V)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.autograd.backward(outs, [gos[i] for i in idx])
+        e1.record()
+        torch.cuda.synchronize(dev)
+        if it >= 3:
+            ts.append(e0.elapsed_time(e1))
+    return sorted(ts)[len(ts) // 2]
+res["ms"]["all stages backward only (one launch + autograd glue)"] = bwd_only(range(len(stages)))
+res["bwd_only_ms_per_stage"] = {f"c{c}_S{S}": bwd_only([i]) for i, (c, S) in enumerate(stages)}
 tot_bytes = sum(s["bytes_fwd"] for s in res["stages"])
 res["all_stages_fwd_gbs_one_launch"] = tot_bytes / res["ms"]["all stages forward, ONE launch (afb_embed_multi_fwd)"] / 1e6
 res["all_stages_fwd_frac_of_hbm"] = res["all_stages_fwd_gbs_one_launch"] / hbm
