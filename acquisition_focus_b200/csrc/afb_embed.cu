@@ -314,8 +314,19 @@ embed_fwd_fused_kernel(const __grid_constant__ EmbedBatch eb, const EmbedView* _
     const float t0 = t[0];                                           // d ix / d w in index units
     const bool flat = fabsf(t0) * Sf < 0.05f;                        // ix changes by < 0.05 voxel along the whole row
     const float* __restrict__ xs = sg.x + (size_t)bv * c * S2;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int row = r0 + warp; row < r1; row += ETHREADS / 32) {
+    // work item = (candidate k along w, row, group of ECG channels), k fastest: neighbouring lanes store neighbouring voxels, and
+    // the c channels of a candidate are spread over threads (a chunk has only rows x ~3 candidates: one thread per candidate
+    // with a serial channel loop left 9 of 10 threads idle behind a 4-round dependent gather chain; the tap arithmetic is
+    // recomputed per channel group instead)
+    constexpr int ECG = 4;
+    const int Kc = flat ? S : min(S, (int)(2.1f / fabsf(t0)) + 2);
+    const int ngroups = (c + ECG - 1) / ECG;
+    const int per_group = (r1 - r0) * Kc;
+    const int items = per_group * ngroups;
+    for (int it = threadIdx.x; it < items; it += ETHREADS) {
+        const int cg = it / per_group, rem = it - cg * per_group;
+        const int rr = rem / Kc, k = rem - rr * Kc;
+        const int row = r0 + rr;
         const int d = row / S, h = row - d * S;
         const float g0 = t[0] * a0 + t[1] * (a1 * h + a0) + t[2] * (a1 * d + a0) + t[3];      // grid x at w = 0 (closed form)
         const float ix0 = ((g0 + 1.0f) * Sf - 1.0f) * 0.5f;
@@ -327,33 +338,39 @@ embed_fwd_fused_kernel(const __grid_constant__ EmbedBatch eb, const EmbedView* _
             lo = max(0, (int)ceilf(wc - half));
             hi = min(S - 1, (int)floorf(wc + half));
         }
-        const float by = base_coord(h, ax), bz = base_coord(d, ax);
-        for (int w = lo + lane; w <= hi; w += 32) {
-            const Tap tp = taps_of(t, base_coord(w, ax), by, bz, S);
-            if (tp.inb == 0u) continue;
-            float* __restrict__ o = ob + (size_t)row * S + w;
-#pragma unroll 4
-            for (int ch = 0; ch < c; ++ch) {
-                const float* __restrict__ xc = xs + (size_t)ch * S2;
-                float acc = 0.0f;
+        const int w = lo + k;
+        if (w > hi) continue;
+        const Tap tp = taps_of(t, base_coord(w, ax), base_coord(h, ax), base_coord(d, ax), S);
+        if (tp.inb == 0u) continue;
+        const int ch0 = cg * ECG;
+        float* __restrict__ o = ob + (size_t)ch0 * S3 + (size_t)row * S + w;
+        const float* __restrict__ xc = xs + (size_t)ch0 * S2;
+        float acc[ECG];
+#pragma unroll
+        for (int j = 0; j < ECG; ++j) {
+            acc[j] = 0.0f;
+            if (ch0 + j < c) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
-                    if ((tp.inb >> q) & 1u) acc = __fadd_rn(acc, __fmul_rn(__ldg(xc + tp.off[q]), tp.w[q]));
-                o[(size_t)ch * S3] = acc;
+                    if ((tp.inb >> q) & 1u) acc[j] = __fadd_rn(acc[j], __fmul_rn(__ldg(xc + (size_t)j * S2 + tp.off[q]), tp.w[q]));
             }
         }
+#pragma unroll
+        for (int j = 0; j < ECG; ++j)
+            if (ch0 + j < c) o[(size_t)j * S3] = acc[j];
     }
 }
 
 // backward, all stages in one launch: GATHER over the 2-D feature-map pixels per (stage, pixel tile, channel chunk,
 // b*V + v); the 12 sums of d(theta) are accumulated over ALL stages (the chain through inverse() and the column normalisation
 // is linear in them) and chained once by the last CTA of each (b,v).
-__global__ void __launch_bounds__(ETHREADS)
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 embed_bwd_fused_kernel(const __grid_constant__ EmbedBatch eb, const EmbedView* __restrict__ views, float* __restrict__ d_aff,
                        double* __restrict__ ws_acc, unsigned* __restrict__ ws_counter, unsigned ctas_per_bv) {
     __shared__ EmbedView ev;
     __shared__ float base[256];
-    __shared__ float red[ETHREADS / 32][12];
+    __shared__ float red[NT / 32][12];
     __shared__ double dT[12];
     __shared__ bool is_last;
     const int si = stage_of_cta(eb, blockIdx.x);
@@ -367,16 +384,16 @@ embed_bwd_fused_kernel(const __grid_constant__ EmbedBatch eb, const EmbedView* _
     {
         const unsigned* __restrict__ src = reinterpret_cast<const unsigned*>(views + bv);
         unsigned* dst = reinterpret_cast<unsigned*>(&ev);
-        for (int i = threadIdx.x; i < (int)(sizeof(EmbedView) / 4); i += ETHREADS) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < (int)(sizeof(EmbedView) / 4); i += NT) dst[i] = __ldg(src + i);
     }
     const AxisConst ax = make_axis_dev(S);
     const bool use_tab = S <= 256;
-    if (use_tab) for (int i = threadIdx.x; i < S; i += ETHREADS) base[i] = base_coord(i, ax);
+    if (use_tab) for (int i = threadIdx.x; i < S; i += NT) base[i] = base_coord(i, ax);
     __syncthreads();
     float part[12];
 #pragma unroll
     for (int q = 0; q < 12; ++q) part[q] = 0.0f;
-    const int pix = tile * ETHREADS + threadIdx.x;
+    const int pix = tile * NT + threadIdx.x;
     const int c0 = cchunk * ECH;
     const int nch = min(ECH, c - c0);
     const size_t S2 = (size_t)S * S, S3 = S2 * S;
@@ -491,7 +508,7 @@ embed_bwd_fused_kernel(const __grid_constant__ EmbedBatch eb, const EmbedView* _
     if (threadIdx.x < 12) {
         double tsum = 0.0;
 #pragma unroll
-        for (int ww = 0; ww < ETHREADS / 32; ++ww) tsum += (double)red[ww][threadIdx.x];
+        for (int ww = 0; ww < NT / 32; ++ww) tsum += (double)red[ww][threadIdx.x];
         if (tsum != 0.0) atomicAdd(ws_acc + (size_t)bv * 16 + threadIdx.x, tsum);
     }
     __threadfence();
@@ -614,6 +631,10 @@ extern "C" int afb_embed_multi_bwd(int n_stages, const float* const* grad_out, c
     if (!d_x && !d_affines) return AFB_EINVAL;
     int rc = check_batch(n_stages, c, S, B, V);
     if (rc != AFB_OK) return rc;
+    static const int variant = [] { const char* e = getenv("AFB_EMBED_BWD_VARIANT"); return e ? atoi(e) : 0; }();
+    // measured (profiles/r2_ab_embed_bwd.jsonl): 256 x 2 and 128 x 4 CTAs/SM tie (0.388 ms, 128 registers); forcing 3 x 256 or
+    // 5 x 128 CTAs/SM (80 / 96 registers, spills inside the match loop) is 1.8x slower
+    const int nt = variant == 1 ? 128 : 256;
     EmbedBatch eb;
     eb.n = 0; eb.B = B; eb.V = V;
     unsigned long long cta = 0, per_bv = 0;
@@ -624,7 +645,7 @@ extern "C" int afb_embed_multi_bwd(int n_stages, const float* const* grad_out, c
         sg.x = x[i]; sg.out = nullptr; sg.go = grad_out[i]; sg.dx = d_x ? d_x[i] : nullptr; sg.c = c[i]; sg.S = S[i];
         sg.rows_per_cta = 0;
         sg.ch_chunks = (c[i] + ECH - 1) / ECH;
-        const unsigned tiles = (unsigned)((S[i] * S[i] + ETHREADS - 1) / ETHREADS);
+        const unsigned tiles = (unsigned)((S[i] * S[i] + nt - 1) / nt);
         sg.chunks = tiles * (unsigned)sg.ch_chunks;
         sg.cta_begin = (unsigned)cta;
         cta += (unsigned long long)sg.chunks * B * V;
@@ -637,6 +658,7 @@ extern "C" int afb_embed_multi_bwd(int n_stages, const float* const* grad_out, c
     unsigned* counter = (unsigned*)(acc + (size_t)B * V * 16);
     EmbedView* views = views_of(workspace, B * V);
     embed_prologue_kernel<<<(B * V + 31) / 32, 32, 0, st>>>(affines, B, V, views);
-    embed_bwd_fused_kernel<<<(unsigned)cta, ETHREADS, 0, st>>>(eb, views, d_affines, acc, counter, (unsigned)per_bv);
+    if (variant == 1) embed_bwd_fused_kernel<128, 4><<<(unsigned)cta, 128, 0, st>>>(eb, views, d_affines, acc, counter, (unsigned)per_bv);
+    else embed_bwd_fused_kernel<256, 2><<<(unsigned)cta, 256, 0, st>>>(eb, views, d_affines, acc, counter, (unsigned)per_bv);
     return (int)cudaGetLastError();
 }
