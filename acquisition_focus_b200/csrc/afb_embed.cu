@@ -291,11 +291,15 @@ embed_fwd_fused_kernel(const __grid_constant__ EmbedBatch eb, const EmbedView* _
     const size_t span = (size_t)(r1 - r0) * S;                        // floats per channel
     const size_t off0 = (size_t)r0 * S;
     if ((S & 3) == 0 && (((uintptr_t)sg.out) & 15u) == 0) {
+        // (channel, 16-byte column) flattened over the threads: at S <= 32 a channel's span is shorter than the CTA
         const int span4 = (int)(span >> 2);
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int ch = 0; ch < c; ++ch) {
-            float4* __restrict__ p = reinterpret_cast<float4*>(ob + (size_t)ch * S3 + off0);
-            for (int i = threadIdx.x; i < span4; i += ETHREADS) __stcs(p + i, z4);
+        const int step_ch = ETHREADS / span4, step_i = ETHREADS - step_ch * span4;
+        int ch = (int)threadIdx.x / span4, i = (int)threadIdx.x - ch * span4;
+        while (ch < c) {
+            __stcs(reinterpret_cast<float4*>(ob + (size_t)ch * S3 + off0) + i, z4);
+            ch += step_ch; i += step_i;
+            if (i >= span4) { i -= span4; ++ch; }
         }
     } else {
         for (int ch = 0; ch < c; ++ch) {
@@ -305,24 +309,27 @@ embed_fwd_fused_kernel(const __grid_constant__ EmbedBatch eb, const EmbedView* _
     }
     __syncthreads();              // orders the zero stores before the patch stores of the same addresses (CTA scope)
     // ---- phase 2: patch the slab voxels of these rows ----
-    float t[12];
-#pragma unroll
-    for (int q = 0; q < 12; ++q) t[q] = __ldg(views[bv].t + q);
-    const AxisConst ax = make_axis_dev(S);
-    const float Sf = (float)S, mid = (float)(S >> 1);
-    const float a1 = 2.0f / Sf, a0 = 1.0f / Sf - 1.0f;              // closed-form base coordinate (2k+1)/S-1 for the row solve
-    const float t0 = t[0];                                           // d ix / d w in index units
-    const bool flat = fabsf(t0) * Sf < 0.05f;                        // ix changes by < 0.05 voxel along the whole row
-    const float* __restrict__ xs = sg.x + (size_t)bv * c * S2;
     // work item = (candidate k along w, row, group of ECG channels), k fastest: neighbouring lanes store neighbouring voxels, and
     // the c channels of a candidate are spread over threads (a chunk has only rows x ~3 candidates: one thread per candidate
     // with a serial channel loop left 9 of 10 threads idle behind a 4-round dependent gather chain; the tap arithmetic is
-    // recomputed per channel group instead)
+    // recomputed per channel group instead).  Threads without an item leave before the per-thread set-up.
+    // (Writing zeros and slab values in ONE full-width store per 16 bytes instead was built and measured: same time -
+    // profiles/experiments/embed_fwd_merged_store.cu.txt.)
     constexpr int ECG = 4;
+    const float Sf = (float)S, mid = (float)(S >> 1);
+    const float t0 = __ldg(views[bv].t + 0);                          // d ix / d w in index units
+    const bool flat = fabsf(t0) * Sf < 0.05f;                        // ix changes by < 0.05 voxel along the whole row
     const int Kc = flat ? S : min(S, (int)(2.1f / fabsf(t0)) + 2);
     const int ngroups = (c + ECG - 1) / ECG;
     const int per_group = (r1 - r0) * Kc;
     const int items = per_group * ngroups;
+    if ((int)threadIdx.x >= items) return;
+    float t[12];
+#pragma unroll
+    for (int q = 0; q < 12; ++q) t[q] = __ldg(views[bv].t + q);
+    const AxisConst ax = make_axis_dev(S);
+    const float a1 = 2.0f / Sf, a0 = 1.0f / Sf - 1.0f;              // closed-form base coordinate (2k+1)/S-1 for the row solve
+    const float* __restrict__ xs = sg.x + (size_t)bv * c * S2;
     for (int it = threadIdx.x; it < items; it += ETHREADS) {
         const int cg = it / per_group, rem = it - cg * per_group;
         const int rr = rem / Kc, k = rem - rr * Kc;
@@ -598,6 +605,8 @@ extern "C" int afb_embed_multi_fwd(int n_stages, const float* const* x, const in
     if (!x || !c || !S || !out || !affines || !workspace) return AFB_EINVAL;
     int rc = check_batch(n_stages, c, S, B, V);
     if (rc != AFB_OK) return rc;
+    const char* ck = getenv("AFB_EMBED_FWD_CHUNK_KB");      // A/B knob (profiles/ab_embed_chunk.py)
+    const long long chunk_bytes = (ck && atoi(ck) > 0 ? atoi(ck) : 32) * 1024ll;
     EmbedBatch eb;
     eb.n = n_stages; eb.B = B; eb.V = V;
     unsigned long long cta = 0;
@@ -605,9 +614,9 @@ extern "C" int afb_embed_multi_fwd(int n_stages, const float* const* x, const in
         if (!x[i] || !out[i]) return AFB_EINVAL;
         EmbedStage& sg = eb.st[i];
         sg.x = x[i]; sg.out = out[i]; sg.go = nullptr; sg.dx = nullptr; sg.c = c[i]; sg.S = S[i]; sg.ch_chunks = 1;
-        // ~64 KB of output per CTA (all channels of its rows), at least one row, at most all rows
+        // ~32 KB of output per CTA (all channels of its rows; swept in profiles/r2_ab_embed_chunk.json), at least one row, at most all rows
         const long long row_bytes = (long long)c[i] * S[i] * 4;
-        long long rpc = (64 * 1024 + row_bytes - 1) / row_bytes;
+        long long rpc = (chunk_bytes + row_bytes - 1) / row_bytes;
         const long long nrows = (long long)S[i] * S[i];
         if (rpc < 1) rpc = 1;
         if (rpc > nrows) rpc = nrows;

@@ -862,9 +862,10 @@ def embed_slices(x: torch.Tensor, affines: torch.Tensor, n_views: int) -> torch.
     """``SkipConnector.forward`` (models/hybrid_unet.py:71-94).
 
     x ``[B, V*c, S, S]``, affines ``[V, B, 4, 4]`` (stacked ``b_grid_affines``) -> ``[B, V*c, S, S, S]``.
-    One stage: zero kernel + slab kernel (measured faster stand-alone: 0.41 vs 0.47 ms at S = 128, c = 16, B x V = 12); all
-    stages of a U-Net pass at once: :func:`embed_slices_multi` (one launch each way, 0.84 vs 0.87 ms forward, 1.66 vs 2.6 ms
-    forward + backward).  ``AFB_EMBED_SINGLE_PASS=1`` routes this call through the batched kernels too (A/B)."""
+    One stage: zero kernel + slab kernel (stand-alone on a par with the batched kernel: 0.41 vs 0.42 ms at S = 128, c = 16,
+    B x V = 12); all stages of a U-Net pass at once: :func:`embed_slices_multi` (one launch each way, 0.64 vs 0.93 ms forward,
+    1.06 vs 1.96 ms forward + backward).  The backward is the batched gather kernel in both cases.
+    ``AFB_EMBED_SINGLE_PASS=1`` routes this call through the batched kernels too (A/B)."""
     if os.environ.get("AFB_EMBED_SINGLE_PASS", "0") == "1":
         return _EmbedMultiFn.apply(affines, n_views, x)[0]
     return _EmbedFn.apply(x, affines, n_views)
