@@ -518,11 +518,26 @@ static int channels_last_vec(const afb_volume* vol, int elem_bytes, const void* 
 // (0.340 vs 0.303 ms soft labels, 0.245 vs 0.217 ms int64 labels at 384 slices) - the kernel is bound by DRAM-miss
 // latency x loads in flight, and the wider vectors cost a resident CTA per SM.  The backward keeps LDG.256.
 template <typename T>
+static bool Do3d_vb32(const afb_volume* vol, const OutGeom& g) {
+    if (sizeof(T) != 4 || !Widen<T>::is_float || g.Do <= 1) return false;
+    const char* e = getenv("AFB_FWD3D_VB");          // A/B knob (profiles/ab_f1_resample.py): 16 = the slices' LDG.128 pairs
+    if (e && atoi(e) == 16) return false;
+    return channels_last_vec(vol, 4, nullptr, 32) == 32;
+}
+
+template <typename T>
 static int launch_fwd(const afb_volume* vol, const VolArgs& v, const ViewArgs& a, const OutGeom& g, int mode, int pad_mode,
                       float pad_value, const float* pad_device, void* out, cudaStream_t st) {
     const int S = v.B * a.V;
     const dim3 grid = slice_grid(g, v.B, a.V);
     const int vb = (mode == AFB_NEAREST || Widen<T>::is_float) ? channels_last_vec(vol, (int)sizeof(T), nullptr, 16) : 0;
+    // 3-D outputs (Do > 1: the 128^3 -> 128^3 prescan resample, learnable_transform.py:252-255) of fp32 volumes with C % 8 == 0:
+    // one LDG.256 per corner and lane, 4 corners in flight.  Unlike the single slices (see above) the resample samples every
+    // input voxel ~8 times from L1/L2, it is bound by load instructions and L1 wavefronts rather than by DRAM-miss latency:
+    // measured 0.675 vs 0.79 ms at B = 8 (profiles/r2_ab_f1_resample.json), bitwise the same output
+    if (vb == 16 && mode == AFB_BILINEAR && Do3d_vb32<T>(vol, g)) {
+        slice_fwd_cl_kernel<T, AFB_BILINEAR, Widen<T>::is_float && sizeof(T) == 4 ? 32 : 16, 4><<<grid, NTHREADS, 0, st>>>(v, a, g, pad_mode, pad_value, pad_device, (T*)out);
+    } else
     if (vb == 16 && mode == AFB_NEAREST) {
         slice_fwd_cl_kernel<T, AFB_NEAREST, 16><<<grid, NTHREADS, 0, st>>>(v, a, g, pad_mode, pad_value, pad_device, (T*)out);
     } else if (vb == 16) {

@@ -88,6 +88,29 @@ def test_structured_affines_tie_policy_bitwise_vs_aten_cpu(afb, name, sizes):
     assert torch.equal(out.cpu(), ref), f"nearest: {(out.cpu() != ref).sum().item()} of {ref.numel()} differ"
 
 
+@pytest.mark.parametrize("name", ["identity", "half_voxel_shift", "zoom2", "random"])
+def test_channels_last_3d_resample_bitwise_vs_aten_cpu(afb, name, monkeypatch):
+    """3-D -> 3-D resample of a channels-last fp32 volume with C = 8 (the prescan resample, learnable_transform.py:252-255): takes
+    the LDG.256 forward (one 32-byte gather per corner); bitwise ATen on the CPU for the same fp32 affine, and bitwise the
+    LDG.128 kernel the slices use (AFB_FWD3D_VB=16)."""
+    D = 32
+    if name == "random":
+        th = (torch.eye(3, 4) + 0.25 * cases.randn((3, 4), 901))[None].float()
+    else:
+        th = torch.tensor(STRUCTURED[name], dtype=torch.float32)[None]
+    vol = cases.randn((2, 8, D, D, D), 900).contiguous(memory_format=torch.channels_last_3d)
+    th2 = th.repeat(2, 1, 1)
+    ref = F.grid_sample(vol, F.affine_grid(th2, [2, 8, D, D, D], align_corners=False), mode="bilinear", padding_mode="zeros",
+                        align_corners=False)
+    vc = vol.cuda()
+    assert vc.stride(1) == 1
+    out = afb.affine_grid_sample(vc, th2.cuda(), (D, D, D), "bilinear")
+    assert torch.equal(out.cpu(), ref), f"{(out.cpu() != ref).sum().item()} of {ref.numel()} differ"
+    monkeypatch.setenv("AFB_FWD3D_VB", "16")
+    out16 = afb.affine_grid_sample(vc, th2.cuda(), (D, D, D), "bilinear")
+    assert torch.equal(out16, out)
+
+
 @pytest.mark.parametrize("shape", SHAPES[:3] + SHAPES[5:])
 def test_affine_grid_sample_backward(afb, shape):
     N, C, D, H, W, Do, Ho, Wo = shape
