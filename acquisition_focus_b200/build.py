@@ -18,7 +18,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libafb200.so")
-SOURCES = ["afb_slice.cu", "afb_views.cu", "afb_embed.cu", "afb_misc.cu", "afb_onehot.cu", "afb_minmask.cu", "afb_aux.cu", "afb_peer.cu"]
+SOURCES = ["afb_slice.cu", "afb_views.cu", "afb_embed.cu", "afb_misc.cu", "afb_onehot.cu", "afb_minmask.cu", "afb_aux.cu", "afb_peer.cu", "afb_host.cpp"]
 HEADERS = [os.path.join(CSRC, "afb_device.cuh"), os.path.join(CSRC, "afb_sampler.cuh"), os.path.join(ROOT, "include", "afb200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

@@ -20,8 +20,9 @@ The per-rank step (collectives included) is captured once into a CUDA graph (`gr
 volumes per GPU the eager step is bound by ~0.5 ms of host launch time, not by the GPU.
 
 `value`  : slices/s with inputs resident in HBM (device timed, CUDA events, max over ranks).
-`e2e`    : same metric through the public API from HOST buffers: pinned index-label + image volumes are copied
-           H2D inside the timed region, expanded to one-hot on the device (as running/run_dl.py:261-264 does),
+`e2e`    : same metric through the public API from HOST buffers: pinned int64 index-label + image volumes are (labels packed to
+           uint8 on the host cores, then) copied H2D inside the timed region, expanded to one-hot on the device (as
+           running/run_dl.py:261-264 does),
            and the reduced parameter gradients + grid affines are read back D2H every step.
 `--impl reference` times the oracle port of the reference's own torch-CPU path on the host cores.
 """
@@ -64,6 +65,8 @@ def parse():
     ap.add_argument("--views", type=int, default=6)
     ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--e2e-group", type=int, default=8, help="volumes per PCIe upload group of the e2e leg")
+    ap.add_argument("--e2e-narrow", type=int, default=1,
+                    help="1: pack the int64 host label maps to uint8 on the host cores before the upload (default); 0: upload int64")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
@@ -707,7 +710,8 @@ def run_e2e(args, AF, par, wl, dev, world, total, sync_all):
     params = wl.params
 
     from acquisition_focus_b200.running.host_input import HostInputPipeline
-    pipe = HostInputPipeline(NUM_CLASSES, dev, depth=2, group_volumes=args.e2e_group)
+    pipe = HostInputPipeline(NUM_CLASSES, dev, depth=2, group_volumes=args.e2e_group, narrow_labels=bool(args.e2e_narrow))
+    host_bytes = h2d
 
     def consume(db):
         soft_t = db.soft_label.detach().requires_grad_(True)
@@ -737,12 +741,20 @@ def run_e2e(args, AF, par, wl, dev, world, total, sync_all):
     run(2)                                   # warm-up (allocates the two buffer sets)
     K = max(2, args.e2e_steps)
     ms = time_steps(lambda: run(K), 1, dev, world, sync_all) / K
+    h2d = pipe.h2d_bytes_last               # what actually crossed PCIe per batch (labels packed to uint8 on the host, or not)
+    narrow_threads = pipe.narrow_threads if pipe.narrow else 0
+    pack_ms, enqueue_ms = pipe.pack_seconds_last * 1e3, pipe.enqueue_seconds_last * 1e3
     del pipe
     return {"value": total * V / (ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "steps": K, "ms_per_step": ms, "h2d_gbs_per_rank": h2d / (ms * 1e-3) / 1e9,
+            "host_input_bytes_per_step": int(host_bytes), "host_input_gbs_per_rank": host_bytes / (ms * 1e-3) / 1e9,
+            "host_label_packing": ({"threads": narrow_threads, "pack_ms_per_batch": pack_ms, "worker_ms_per_batch": enqueue_ms, "what": "int64 -> uint8 on the host cores (afb_host_narrow_labels), on a worker "
+                                    "thread, group by group, overlapped with the uploads and with the previous step"}
+                                   if narrow_threads else None),
             "timed_region": "K steps incl. the pipeline fill: every consumed batch is uploaded inside it (K uploads, K fwd+bwd, K D2H)",
             "bytes_are": "per rank (each rank uploads its own shard)",
-            "what": "pinned host index-label int64 + image fp32 -> running.host_input.HostInputPipeline (double buffered: H2D in groups of "
+            "what": "pinned host index-label int64 + image fp32 -> running.host_input.HostInputPipeline (labels packed to uint8 on the host "
+                    "unless --e2e-narrow 0; double buffered: H2D in groups of "
                     f"{args.e2e_group} volumes on a copy stream, fused one-hot expansion + min record of the arrived groups on an expansion "
                     "stream, overlapped with the previous step's slicing) -> same acquisition fwd+bwd (dVolume + dTheta) -> D2H reduced "
                     "dTheta + grid affines; one full batch uploaded per step"}

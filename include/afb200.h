@@ -107,6 +107,12 @@ const char* afb_error_string(int code);
  * launch; with n_bytes <= ~32 MiB the buffer is L2 resident and n_bytes*passes/time is the L2 read bandwidth. */
 int afb_probe_read(const void* buf, int64_t n_bytes, int passes, float* sink, void* stream);
 
+/* ---- host-side stage of the upload path (runs on the host cores, no CUDA call) ------------------------------
+ * Packs an integer label map (AFB_I64 | AFB_I32 | AFB_I16; run_dl.py:261 uploads torch.long) to uint8 with n_threads host
+ * threads, so that 1 instead of 8 bytes per voxel cross PCIe; afb_onehot_expand takes the uint8 map.  *out_of_range = 1 when a
+ * value lies outside [0, 255] (the output is then unusable).  src and dst are HOST pointers (pinned or pageable). */
+int afb_host_narrow_labels(const void* src, int src_dtype, int64_t n, uint8_t* dst, int n_threads, int* out_of_range);
+
 /* ---- min pre-pass of the bilinear path (nifti_utils.py:200) -------------------------------- */
 /* Scans n_elements of a dense tensor; writes out_min_count[0] = min as float32,
  * out_min_count[1] = number of elements equal to the min (as float32, exact < 2^24, else rounded).

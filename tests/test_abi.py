@@ -59,3 +59,29 @@ def test_product_does_not_import_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_host_label_packing_runs_without_a_gpu():
+    """afb_host_narrow_labels is host code: int64 / int32 / int16 -> uint8 over several threads, ragged lengths, unaligned
+    sources, and the out-of-range report (negative values and values above 255)."""
+    import ctypes as C
+    import torch
+    from acquisition_focus_b200 import _lib as L
+    from acquisition_focus_b200.running.host_input import narrow_labels_host
+    g = torch.Generator().manual_seed(3)
+    for dt in (torch.int64, torch.int32, torch.int16):
+        for n in (1, 15, 16, 1000003):
+            src = torch.randint(0, 256, (n + 1,), generator=g, dtype=dt)
+            for off in (0, 1):
+                x = src[off:off + n].contiguous() if off == 0 else src[off:off + n]
+                out = torch.empty(n, dtype=torch.uint8)
+                narrow_labels_host(x, out, n_threads=5)
+                assert torch.equal(out, x.to(torch.uint8))
+    x = torch.zeros(200000, dtype=torch.int64)
+    out = torch.empty(200000, dtype=torch.uint8)
+    for bad_value in (256, -1, 1 << 40):
+        x[150001] = bad_value
+        with pytest.raises(ValueError):
+            narrow_labels_host(x, out, n_threads=4)
+    bad = C.c_int(7)
+    assert L.lib().afb_host_narrow_labels(x.data_ptr(), L.DTYPES[torch.float32], 10, out.data_ptr(), 1, C.byref(bad)) != 0

@@ -126,9 +126,11 @@ def test_half_dvolume_cast_is_round_to_nearest_even(afb, dt):
     assert torch.equal(out, x.to(dt))
 
 
-def test_double_buffered_pipeline_equals_single_upload(afb):
+@pytest.mark.parametrize("narrow", [True, False])
+def test_double_buffered_pipeline_equals_single_upload(afb, narrow):
     """HostInputPipeline (next batch uploaded + expanded while the current one is used; slots reused two submits later) hands
-    over, batch after batch, bitwise what upload_one_hot returns, also when a slow consumer delays the slot release."""
+    over, batch after batch, bitwise what upload_one_hot returns, also when a slow consumer delays the slot release - with the
+    int64 label maps packed to uint8 on the host by a worker thread (the default) and with the plain int64 upload."""
     from acquisition_focus_b200.running.host_input import HostInputPipeline, upload_one_hot
     C, B, S = 8, 4, 32
     batches = []
@@ -136,14 +138,16 @@ def test_double_buffered_pipeline_equals_single_upload(afb):
         lab = cases.randint(0, C, (B, S, S, S), 700 + k).pin_memory()
         img = cases.randn((B, 1, S, S, S), 800 + k).pin_memory()
         batches.append((lab, img))
-    pipe = HostInputPipeline(C, "cuda", depth=2, group_volumes=2)
+    pipe = HostInputPipeline(C, "cuda", depth=2, group_volumes=2, narrow_labels=narrow, narrow_threads=3)
     pipe.submit(*batches[0])
+    assert pipe.h2d_bytes_last == batches[0][0].numel() * (1 if narrow else 8) + batches[0][1].numel() * 4
     spin = torch.empty(64 * 1024 * 1024, device="cuda")
     for k in range(5):
         if k + 1 < 5:
             pipe.submit(*batches[k + 1])
         db = pipe.get()
-        got = [db.label_map.clone(), db.label.clone(), db.soft_label.clone(), db.image.clone(), db.soft_pad.clone(), db.image_pad.clone()]
+        assert db.label_map.dtype == (torch.uint8 if narrow else torch.int64)
+        got = [db.label_map.long(), db.label.clone(), db.soft_label.clone(), db.image.clone(), db.soft_pad.clone(), db.image_pad.clone()]
         for _ in range(3):
             spin.add_(1.0)                      # the consumer keeps the compute stream busy before it releases the slot
         chk = db.soft_label.sum()               # ... and still reads the slot afterwards
@@ -153,3 +157,13 @@ def test_double_buffered_pipeline_equals_single_upload(afb):
         for a, b in zip(got, want):
             assert torch.equal(a, b)
         assert chk.item() == ref.soft_label.sum().item()
+
+
+def test_pipeline_rejects_labels_that_do_not_fit_a_byte(afb):
+    from acquisition_focus_b200.running.host_input import HostInputPipeline
+    lab = cases.randint(0, 8, (2, 16, 16, 16), 5).pin_memory()
+    lab[1, 3, 4, 5] = 300
+    pipe = HostInputPipeline(8, "cuda", depth=2, group_volumes=1)
+    pipe.submit(lab, None)
+    with pytest.raises(ValueError, match="outside"):
+        pipe.get()
