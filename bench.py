@@ -65,8 +65,9 @@ def parse():
     ap.add_argument("--views", type=int, default=6)
     ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--e2e-group", type=int, default=8, help="volumes per PCIe upload group of the e2e leg")
-    ap.add_argument("--e2e-narrow", type=int, default=1,
-                    help="1: pack the int64 host label maps to uint8 on the host cores before the upload (default); 0: upload int64")
+    ap.add_argument("--e2e-narrow", type=int, default=-1,
+                    help="1: pack the int64 host label maps to uint8 on the host cores before the upload; 0: upload int64; "
+                         "-1 (default): pack when the rank has >= 8 host cores for it (HostInputPipeline's 'auto')")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
@@ -710,7 +711,10 @@ def run_e2e(args, AF, par, wl, dev, world, total, sync_all):
     params = wl.params
 
     from acquisition_focus_b200.running.host_input import HostInputPipeline
-    pipe = HostInputPipeline(NUM_CLASSES, dev, depth=2, group_volumes=args.e2e_group, narrow_labels=bool(args.e2e_narrow))
+    # N > 1: _pin_to_local_cpus gave this rank its OWN share of the NUMA-local cores - the packing pass may use all of them
+    nthr = min(16, len(os.sched_getaffinity(0))) if world > 1 and not os.environ.get("AFB_NARROW_THREADS") else None
+    pipe = HostInputPipeline(NUM_CLASSES, dev, depth=2, group_volumes=args.e2e_group, narrow_labels=("auto" if args.e2e_narrow < 0 else bool(args.e2e_narrow)),
+                             narrow_threads=nthr)
     host_bytes = h2d
 
     def consume(db):
@@ -743,18 +747,21 @@ def run_e2e(args, AF, par, wl, dev, world, total, sync_all):
     ms = time_steps(lambda: run(K), 1, dev, world, sync_all) / K
     h2d = pipe.h2d_bytes_last               # what actually crossed PCIe per batch (labels packed to uint8 on the host, or not)
     narrow_threads = pipe.narrow_threads if pipe.narrow else 0
+    nthr = pipe.narrow_threads
     pack_ms, enqueue_ms = pipe.pack_seconds_last * 1e3, pipe.enqueue_seconds_last * 1e3
     del pipe
     return {"value": total * V / (ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "steps": K, "ms_per_step": ms, "h2d_gbs_per_rank": h2d / (ms * 1e-3) / 1e9,
             "host_input_bytes_per_step": int(host_bytes), "host_input_gbs_per_rank": host_bytes / (ms * 1e-3) / 1e9,
+            "host_cores_for_packing": int(nthr or 0) or None,
             "host_label_packing": ({"threads": narrow_threads, "pack_ms_per_batch": pack_ms, "worker_ms_per_batch": enqueue_ms, "what": "int64 -> uint8 on the host cores (afb_host_narrow_labels), on a worker "
                                     "thread, group by group, overlapped with the uploads and with the previous step"}
                                    if narrow_threads else None),
             "timed_region": "K steps incl. the pipeline fill: every consumed batch is uploaded inside it (K uploads, K fwd+bwd, K D2H)",
             "bytes_are": "per rank (each rank uploads its own shard)",
             "what": "pinned host index-label int64 + image fp32 -> running.host_input.HostInputPipeline (labels packed to uint8 on the host "
-                    "unless --e2e-narrow 0; double buffered: H2D in groups of "
+                    "cores when host_label_packing is not null: --e2e-narrow, default auto = when the rank has >= 8 host cores; double "
+                    "buffered: H2D in groups of "
                     f"{args.e2e_group} volumes on a copy stream, fused one-hot expansion + min record of the arrived groups on an expansion "
                     "stream, overlapped with the previous step's slicing) -> same acquisition fwd+bwd (dVolume + dTheta) -> D2H reduced "
                     "dTheta + grid affines; one full batch uploaded per step"}
