@@ -157,7 +157,7 @@ extern "C" int afb_slice_onehot_fwd(const afb_volume* labels, int num_classes, c
     if (!y_soft && label_out == 0) return AFB_EINVAL;
     if (label_out != 0 && !y_label) return AFB_EINVAL;
     if ((long long)num_classes * Do * Ho * Wo >= 2147483647ll) return AFB_EUNSUPPORTED;     // 32-bit channel offsets
-    const OutGeom g = make_geom(Do, Ho, Wo);
+    const OutGeom g = make_geom(Do, Ho, Wo, /*allow_wide=*/false);
     cudaStream_t st = (cudaStream_t)stream;
     switch (labels->dtype) {
         case AFB_U8: return launch_onehot_fwd<uint8_t>(la, a, g, y_soft, y_label, label_out, st);
@@ -179,7 +179,7 @@ extern "C" int afb_slice_onehot_bwd(const afb_volume* labels, int num_classes, c
     if (!workspace || (!grad_y_soft && !grad_grid_affine) || !d_affine) return AFB_EINVAL;
     if (a.kind == AFB_AFFINE_PARAMS && !views->params) return AFB_EINVAL;
     if ((long long)num_classes * Do * Ho * Wo >= 2147483647ll) return AFB_EUNSUPPORTED;     // 32-bit channel offsets
-    const OutGeom g = make_geom(Do, Ho, Wo);
+    const OutGeom g = make_geom(Do, Ho, Wo, /*allow_wide=*/false);
     const int S = la.B * a.V;
     const dim3 grid = slice_grid(g, la.B, a.V);
     double* acc = (double*)workspace;
