@@ -63,8 +63,9 @@ def parse():
     ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the additional weak-scaling measurement")
     ap.add_argument("--views", type=int, default=6)
-    ap.add_argument("--e2e-steps", type=int, default=12)
+    ap.add_argument("--e2e-steps", type=int, default=24, help="steps of the e2e leg (its timed region includes the pipeline fill)")
     ap.add_argument("--e2e-group", type=int, default=8, help="volumes per PCIe upload group of the e2e leg")
+    ap.add_argument("--e2e-depth", type=int, default=3, help="device buffer sets of the e2e upload pipeline (batches in flight)")
     ap.add_argument("--e2e-narrow", type=int, default=-1,
                     help="1: pack the int64 host label maps to uint8 on the host cores before the upload; 0: upload int64; "
                          "-1 (default): pack when the rank has >= 8 host cores for it (HostInputPipeline's 'auto')")
@@ -713,7 +714,8 @@ def run_e2e(args, AF, par, wl, dev, world, total, sync_all):
     from acquisition_focus_b200.running.host_input import HostInputPipeline
     # N > 1: _pin_to_local_cpus gave this rank its OWN share of the NUMA-local cores - the packing pass may use all of them
     nthr = min(16, len(os.sched_getaffinity(0))) if world > 1 and not os.environ.get("AFB_NARROW_THREADS") else None
-    pipe = HostInputPipeline(NUM_CLASSES, dev, depth=2, group_volumes=args.e2e_group, narrow_labels=("auto" if args.e2e_narrow < 0 else bool(args.e2e_narrow)),
+    depth = max(2, args.e2e_depth)
+    pipe = HostInputPipeline(NUM_CLASSES, dev, depth=depth, group_volumes=args.e2e_group, narrow_labels=("auto" if args.e2e_narrow < 0 else bool(args.e2e_narrow)),
                              narrow_threads=nthr)
     host_bytes = h2d
 
@@ -735,14 +737,17 @@ def run_e2e(args, AF, par, wl, dev, world, total, sync_all):
         # (groups of volumes; the groups that have arrived are expanded to the int64 + fp32 one-hot volumes of run_dl.py:261-264
         # together with the soft volume's min record on an expansion stream).  The upload of EVERY consumed batch - the first
         # one included - is issued inside this function, i.e. inside the timed region: K steps = K full uploads + K fwd/bwd.
-        pipe.submit(host_lab, host_img)
+        # `depth - 1` batches are in flight ahead of the one being consumed (a slot is reused `depth` submits later)
+        ahead = depth - 1
+        for j in range(min(ahead, K)):
+            pipe.submit(host_lab, host_img)
         for k in range(K):
-            if k + 1 < K:
+            if k + ahead < K:
                 pipe.submit(host_lab, host_img)
             consume(pipe.get())
 
     wl.free_dense()
-    run(2)                                   # warm-up (allocates the two buffer sets)
+    run(depth)                               # warm-up (allocates the buffer sets)
     K = max(2, args.e2e_steps)
     ms = time_steps(lambda: run(K), 1, dev, world, sync_all) / K
     h2d = pipe.h2d_bytes_last               # what actually crossed PCIe per batch (labels packed to uint8 on the host, or not)
@@ -751,7 +756,7 @@ def run_e2e(args, AF, par, wl, dev, world, total, sync_all):
     pack_ms, enqueue_ms = pipe.pack_seconds_last * 1e3, pipe.enqueue_seconds_last * 1e3
     del pipe
     return {"value": total * V / (ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "steps": K, "ms_per_step": ms, "h2d_gbs_per_rank": h2d / (ms * 1e-3) / 1e9,
+            "steps": K, "ms_per_step": ms, "h2d_gbs_per_rank": h2d / (ms * 1e-3) / 1e9, "pipeline_depth": depth,
             "host_input_bytes_per_step": int(host_bytes), "host_input_gbs_per_rank": host_bytes / (ms * 1e-3) / 1e9,
             "host_cores_for_packing": int(nthr or 0) or None,
             "host_label_packing": ({"threads": narrow_threads, "pack_ms_per_batch": pack_ms, "worker_ms_per_batch": enqueue_ms, "what": "int64 -> uint8 on the host cores (afb_host_narrow_labels), on a worker "
