@@ -126,16 +126,22 @@ class HostInputPipeline:
 
     def __init__(self, num_classes: int, device, depth: int = 2, group_volumes: int = 8, want_label: bool = True,
                  narrow_labels="auto", narrow_threads: Optional[int] = None, pack_volumes: int = 64):
-        """``narrow_labels``: True / False, or "auto" (default): pack the label maps on the host only when this process has at
-        least ``MIN_PACK_THREADS`` host threads for it.  Measured (64 volumes of 128^3 in total, profiles/r2_bench_*): one GPU
-        with 16 host cores 26.1 k slices/s packed against 13.1 k with the int64 upload; eight GPUs sharing 32 host cores
-        (4 per rank) 34.4 k packed against 43.5 k - there the cores, not the link, are what is short."""
+        """``narrow_labels``: False (upload the label maps as they are), True (pack all of them to uint8 on the host first),
+        "split" (the host cores pack a share of each batch WHILE the link carries the images and the rest of the maps as int64;
+        the share follows the measured packing and link rates) or "auto" (default: "split" when there are >= 2 host threads).
+        Measured, 64 volumes of 128^3 per step on one GPU (profiles/r2_e2e_modes.jsonl): 16 host threads - int64 upload 29.4 ms,
+        split 13.4 ms (all 64 packed); 3 host threads - int64 upload 29.4, all packed 23.9, split 20.6 ms (44 of 64 packed)."""
         self.C, self.device, self.depth = int(num_classes), torch.device(device), int(depth)
         self.group_volumes, self.want_label = int(group_volumes), want_label
         self.narrow_threads = int(narrow_threads or default_narrow_threads())
         if narrow_labels == "auto":
-            narrow_labels = self.narrow_threads >= self.MIN_PACK_THREADS
+            narrow_labels = "split" if self.narrow_threads >= 2 else False
+        self.split = narrow_labels == "split"
         self.narrow = bool(narrow_labels) and self.C <= 256
+        # split uploads: share of a batch's volumes that is packed on the host (the rest crosses PCIe as int64 meanwhile);
+        # adapted from the measured packing and link rates so that both finish together
+        self.pack_fraction = 1.0 if self.narrow_threads >= self.MIN_PACK_THREADS else 0.5
+        self._r_pack = self._r_link = None             # bytes/s: int64 bytes packed per second, bytes copied per second
         self.pack_volumes = int(os.environ.get("AFB_PACK_VOLUMES", pack_volumes))
         with torch.cuda.device(self.device):
             self.copy = torch.cuda.Stream(self.device)
@@ -146,6 +152,7 @@ class HostInputPipeline:
         self.n_submitted = 0
         self.h2d_bytes_last = 0                        # bytes the last submitted batch moves over PCIe
         self.pack_seconds_last = self.enqueue_seconds_last = 0.0      # host time of the last batch: packing / whole enqueue
+        self.packed_volumes_last = None                # split uploads: volumes of the last batch that were packed
         self._jobs = None                              # FIFO of the ONE worker thread (started with the first packed batch):
         self._worker = None                            # batches are packed one after the other, never two at a time
 
@@ -155,7 +162,7 @@ class HostInputPipeline:
             if job is None:
                 return
             args, finished = job
-            self._enqueue(*args)
+            (self._enqueue_split if self.split else self._enqueue)(*args)
             finished.set()
 
     def close(self) -> None:
@@ -183,7 +190,10 @@ class HostInputPipeline:
                      "soft": torch.empty(shape + (C_,), dtype=torch.float32, device=dev),
                      "onehot": torch.empty(shape + (C_,), dtype=torch.int64, device=dev) if self.want_label else None,
                      # pinned staging buffer of the packed labels; `copied` = its last H2D copy has finished
-                     "lab8_host": torch.empty(shape, dtype=torch.uint8).pin_memory() if narrow else None, "copied": None}
+                     "lab8_host": torch.empty(shape, dtype=torch.uint8).pin_memory() if narrow else None, "copied": None,
+                     # split uploads: the volumes that are NOT packed arrive here as they are on the host
+                     "lab_raw": torch.empty(shape, dtype=host_label.dtype, device=dev) if (narrow and self.split) else None,
+                     "rate": None}
                 s["record"] = AF.min_record_alloc(s["soft"].numel(), dev)
                 torch.cuda.current_stream(dev).synchronize()          # one-time: the fresh buffers are safe on every stream
             self.slots[i] = s
@@ -234,6 +244,105 @@ class HostInputPipeline:
             holder["db"] = DeviceBatch(s["lab"], s["onehot"].permute(*perm) if self.want_label else None, s["soft"].permute(*perm),
                                        s["img"], soft_pad, image_pad)
             holder["done"] = done
+            self.pack_seconds_last, self.enqueue_seconds_last = t_pack, time.perf_counter() - t_begin
+        except BaseException as e:          # noqa: BLE001 - re-raised on the caller's thread by get()
+            holder["error"] = e
+
+    def _enqueue_split(self, i, s, host_label, host_image, narrow, holder):
+        """Split upload of one batch (worker thread): the link carries the images and the int64 label maps of the volumes that are
+        not packed WHILE the host cores pack the others; the packed maps follow.  The share is set so that both finish together:
+        with L, I bytes of int64 labels and images, r_pack the packing rate (int64 bytes/s) and r_link the copy rate,
+        f = (I + L) / (L * (r_link / r_pack + 7/8)), clamped to [0, 1] and rounded to whole volumes; both rates are measured on
+        every batch (host clock around the packing calls, CUDA events around the first phase of copies)."""
+        try:
+            t_begin = time.perf_counter()
+            B = host_label.shape[0]
+            vox = host_label[0].numel()
+            per_vol = vox * self.C
+            gv = B if per_vol % 512 else max(1, min(self.group_volumes, B))
+            esz = host_label.element_size()
+            L_bytes = B * vox * esz
+            I_bytes = host_image.numel() * host_image.element_size() if host_image is not None else 0
+            with torch.cuda.device(self.device):
+                if self.free_events[i] is not None:
+                    self.copy.wait_event(self.free_events[i])
+                    self.expand.wait_event(self.free_events[i])
+                if s["copied"] is not None:
+                    s["copied"].synchronize()
+                    if s["rate"] is not None:                   # link rate seen by this slot's previous batch
+                        e0, e1, nbytes = s["rate"]
+                        ms = e0.elapsed_time(e1)
+                        if ms > 0 and nbytes > 0:
+                            r = nbytes / (ms * 1e-3)
+                            self._r_link = r if self._r_link is None else 0.5 * (self._r_link + r)
+                if self._r_pack and self._r_link and B * vox * esz > 0:
+                    f = (I_bytes + L_bytes) / (L_bytes * (self._r_link / self._r_pack + 1.0 - 1.0 / esz))
+                    self.pack_fraction = min(1.0, max(0.0, 0.5 * (self.pack_fraction + f)))
+                n_pack = int(round(self.pack_fraction * B))
+                n_pack = (n_pack // gv) * gv if per_vol % 512 else n_pack      # ragged volumes: whole groups only
+                n_pack = min(B, max(0, n_pack))
+                lab8, raw = s["lab"], s["lab_raw"]
+                # ---- phase 1 (link): images + the int64 maps of volumes [n_pack, B) ----
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(self.copy)
+                bytes1 = 0
+                arrived = {}
+                for b0 in range(0, B, gv):
+                    b1 = min(B, b0 + gv)
+                    with torch.cuda.stream(self.copy):
+                        if s["img"] is not None:
+                            s["img"][b0:b1].copy_(host_image[b0:b1], non_blocking=True)
+                            bytes1 += (b1 - b0) * host_image[0].numel() * host_image.element_size()
+                        r0 = max(b0, n_pack)
+                        if r0 < b1:
+                            raw[r0:b1].copy_(host_label[r0:b1], non_blocking=True)
+                            bytes1 += (b1 - r0) * vox * esz
+                            arrived[("raw", b0)] = self.copy.record_event()
+                e1.record(self.copy)
+                s["rate"] = (e0, e1, bytes1)
+                def expand(kind, lo, hi, src, b0):
+                    self.expand.wait_event(arrived[(kind, b0)])
+                    with torch.cuda.stream(self.expand):
+                        AF.onehot_expand(src[lo:hi], self.C, out_label=s["onehot"][lo:hi] if self.want_label else None,
+                                         out_soft=s["soft"][lo:hi], record=s["record"], total_elements=s["soft"].numel(),
+                                         elem_offset=lo * per_vol)
+                        if kind == "raw":
+                            lab8[lo:hi].copy_(src[lo:hi])              # label_map is uint8 for the whole batch
+
+                for b0 in range(0, B, gv):                              # enqueued now: they run while the cores pack
+                    b1 = min(B, b0 + gv)
+                    if max(b0, n_pack) < b1:
+                        expand("raw", max(b0, n_pack), b1, raw, b0)
+                # ---- meanwhile (host cores): pack volumes [0, n_pack) ----
+                t_pack = 0.0
+                if n_pack > 0:
+                    t0 = time.perf_counter()
+                    narrow_labels_host(host_label[:n_pack], s["lab8_host"][:n_pack], self.narrow_threads)
+                    t_pack = time.perf_counter() - t0
+                    r = n_pack * vox * esz / max(t_pack, 1e-9)
+                    self._r_pack = r if self._r_pack is None else 0.5 * (self._r_pack + r)
+                # ---- phase 2 (link): the packed maps, expanded group by group as they arrive ----
+                for b0 in range(0, B, gv):
+                    p1 = min(b0 + gv, n_pack)
+                    if b0 < p1:
+                        with torch.cuda.stream(self.copy):
+                            lab8[b0:p1].copy_(s["lab8_host"][b0:p1], non_blocking=True)
+                            arrived[("packed", b0)] = self.copy.record_event()
+                        expand("packed", b0, p1, lab8, b0)
+                with torch.cuda.stream(self.copy):
+                    last = self.copy.record_event()
+                s["copied"] = last
+                with torch.cuda.stream(self.expand):
+                    soft_pad = AF.min_count_from_record(s["record"], s["soft"].numel())
+                    image_pad = AF.volume_min(s["img"]) if s["img"] is not None else None
+                    done = self.expand.record_event()
+            perm = (0, 4, 1, 2, 3)
+            holder["db"] = DeviceBatch(lab8, s["onehot"].permute(*perm) if self.want_label else None, s["soft"].permute(*perm),
+                                       s["img"], soft_pad, image_pad)
+            holder["done"] = done
+            holder["h2d_bytes"] = I_bytes + n_pack * vox + (B - n_pack) * vox * esz
+            self.h2d_bytes_last = holder["h2d_bytes"]
+            self.packed_volumes_last = n_pack
             self.pack_seconds_last, self.enqueue_seconds_last = t_pack, time.perf_counter() - t_begin
         except BaseException as e:          # noqa: BLE001 - re-raised on the caller's thread by get()
             holder["error"] = e

@@ -67,7 +67,8 @@ def parse():
     ap.add_argument("--e2e-group", type=int, default=8, help="volumes per PCIe upload group of the e2e leg")
     ap.add_argument("--e2e-depth", type=int, default=3, help="device buffer sets of the e2e upload pipeline (batches in flight)")
     ap.add_argument("--e2e-narrow", type=int, default=-1,
-                    help="1: pack the int64 host label maps to uint8 on the host cores before the upload; 0: upload int64; "
+                    help="1: pack the int64 host label maps to uint8 on the host cores before the upload; 0: upload int64; 2: split upload "
+                         "(the cores pack a share of each batch while the link carries the rest as int64; share adapted on line); "
                          "-1 (default): pack when the rank has >= 8 host cores for it (HostInputPipeline's 'auto')")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -715,7 +716,7 @@ def run_e2e(args, AF, par, wl, dev, world, total, sync_all):
     # N > 1: _pin_to_local_cpus gave this rank its OWN share of the NUMA-local cores - the packing pass may use all of them
     nthr = min(16, len(os.sched_getaffinity(0))) if world > 1 and not os.environ.get("AFB_NARROW_THREADS") else None
     depth = max(2, args.e2e_depth)
-    pipe = HostInputPipeline(NUM_CLASSES, dev, depth=depth, group_volumes=args.e2e_group, narrow_labels=("auto" if args.e2e_narrow < 0 else bool(args.e2e_narrow)),
+    pipe = HostInputPipeline(NUM_CLASSES, dev, depth=depth, group_volumes=args.e2e_group, narrow_labels=("auto" if args.e2e_narrow < 0 else "split" if args.e2e_narrow == 2 else bool(args.e2e_narrow)),
                              narrow_threads=nthr)
     host_bytes = h2d
 
@@ -754,11 +755,13 @@ def run_e2e(args, AF, par, wl, dev, world, total, sync_all):
     narrow_threads = pipe.narrow_threads if pipe.narrow else 0
     nthr = pipe.narrow_threads
     pack_ms, enqueue_ms = pipe.pack_seconds_last * 1e3, pipe.enqueue_seconds_last * 1e3
+    split_info = ({"packed_volumes_of_last_batch": pipe.packed_volumes_last, "pack_fraction": pipe.pack_fraction,
+                   "pack_rate_gbs": (pipe._r_pack or 0) / 1e9, "link_rate_gbs": (pipe._r_link or 0) / 1e9} if pipe.split else None)
     del pipe
     return {"value": total * V / (ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "steps": K, "ms_per_step": ms, "h2d_gbs_per_rank": h2d / (ms * 1e-3) / 1e9, "pipeline_depth": depth,
             "host_input_bytes_per_step": int(host_bytes), "host_input_gbs_per_rank": host_bytes / (ms * 1e-3) / 1e9,
-            "host_cores_for_packing": int(nthr or 0) or None,
+            "host_cores_for_packing": int(nthr or 0) or None, "split_upload": split_info,
             "host_label_packing": ({"threads": narrow_threads, "pack_ms_per_batch": pack_ms, "worker_ms_per_batch": enqueue_ms, "what": "int64 -> uint8 on the host cores (afb_host_narrow_labels), on a worker "
                                     "thread, group by group, overlapped with the uploads and with the previous step"}
                                    if narrow_threads else None),

@@ -126,7 +126,7 @@ def test_half_dvolume_cast_is_round_to_nearest_even(afb, dt):
     assert torch.equal(out, x.to(dt))
 
 
-@pytest.mark.parametrize("narrow", [True, False])
+@pytest.mark.parametrize("narrow", [True, False, "split"])
 def test_double_buffered_pipeline_equals_single_upload(afb, narrow):
     """HostInputPipeline (next batch uploaded + expanded while the current one is used; slots reused two submits later) hands
     over, batch after batch, bitwise what upload_one_hot returns, also when a slow consumer delays the slot release - with the
@@ -140,7 +140,10 @@ def test_double_buffered_pipeline_equals_single_upload(afb, narrow):
         batches.append((lab, img))
     pipe = HostInputPipeline(C, "cuda", depth=2, group_volumes=2, narrow_labels=narrow, narrow_threads=3)
     pipe.submit(*batches[0])
-    assert pipe.h2d_bytes_last == batches[0][0].numel() * (1 if narrow else 8) + batches[0][1].numel() * 4
+    if narrow != "split":
+        assert pipe.h2d_bytes_last == batches[0][0].numel() * (1 if narrow else 8) + batches[0][1].numel() * 4
+    else:
+        pipe.pack_fraction = 0.5                # two of the four volumes packed, two uploaded as int64
     spin = torch.empty(64 * 1024 * 1024, device="cuda")
     for k in range(5):
         if k + 1 < 5:
