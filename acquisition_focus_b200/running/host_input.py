@@ -56,6 +56,17 @@ def narrow_labels_host(host_label: torch.Tensor, out: torch.Tensor, n_threads: O
 _NARROWABLE = (torch.int64, torch.int32, torch.int16)
 
 
+def balanced_pack_fraction(image_bytes: float, label_bytes: float, label_elem_size: int, pack_rate: float, link_rate: float) -> float:
+    """Share f of a batch's label volumes to pack on the host so that the cores and the link finish together:
+    cores  f * L / pack_rate        (pack_rate in bytes of the wide labels per second)
+    link   (I + (1 - f) * L + f * L / e) / link_rate        (images, unpacked maps, packed maps; e = bytes per wide label)
+    =>  f = (I + L) / (L * (link_rate / pack_rate + 1 - 1/e)), clamped to [0, 1]."""
+    if label_bytes <= 0 or pack_rate <= 0 or link_rate <= 0:
+        return 0.0
+    f = (image_bytes + label_bytes) / (label_bytes * (link_rate / pack_rate + 1.0 - 1.0 / label_elem_size))
+    return min(1.0, max(0.0, f))
+
+
 class DeviceBatch(NamedTuple):
     label_map: torch.Tensor            # [B,D,H,W] integer (the uploaded index map; uint8 when it was packed on the host)
     label: Optional[torch.Tensor]      # [B,C,D,H,W] int64 one-hot, channels-last strides (as run_dl.py:261-262)
@@ -275,8 +286,8 @@ class HostInputPipeline:
                         if ms > 0 and nbytes > 0:
                             r = nbytes / (ms * 1e-3)
                             self._r_link = r if self._r_link is None else 0.5 * (self._r_link + r)
-                if self._r_pack and self._r_link and B * vox * esz > 0:
-                    f = (I_bytes + L_bytes) / (L_bytes * (self._r_link / self._r_pack + 1.0 - 1.0 / esz))
+                if self._r_pack and self._r_link and L_bytes > 0:
+                    f = balanced_pack_fraction(I_bytes, L_bytes, esz, self._r_pack, self._r_link)
                     self.pack_fraction = min(1.0, max(0.0, 0.5 * (self.pack_fraction + f)))
                 n_pack = int(round(self.pack_fraction * B))
                 n_pack = (n_pack // gv) * gv if per_vol % 512 else n_pack      # ragged volumes: whole groups only

@@ -85,3 +85,19 @@ def test_host_label_packing_runs_without_a_gpu():
             narrow_labels_host(x, out, n_threads=4)
     bad = C.c_int(7)
     assert L.lib().afb_host_narrow_labels(x.data_ptr(), L.DTYPES[torch.float32], 10, out.data_ptr(), 1, C.byref(bad)) != 0
+
+
+def test_split_upload_share_balances_cores_and_link():
+    """HostInputPipeline's split upload: at the returned share the packing pass and the link take the same time (or the share
+    saturates at 0 / 1)."""
+    from acquisition_focus_b200.running.host_input import balanced_pack_fraction
+    L_, I_, e = 1.07e9, 0.54e9, 8
+    for r_pack, r_link in ((41e9, 55e9), (15e9, 16.5e9), (5e9, 55e9), (20e9, 20e9)):
+        f = balanced_pack_fraction(I_, L_, e, r_pack, r_link)
+        assert 0.0 < f < 1.0
+        t_cores = f * L_ / r_pack
+        t_link = (I_ + (1 - f) * L_ + f * L_ / e) / r_link
+        assert abs(t_cores - t_link) < 1e-9 * max(t_cores, 1.0) + 1e-6 * t_link
+    assert balanced_pack_fraction(I_, L_, e, 92e9, 50e9) == 1.0          # enough cores: pack everything (N = 1 on the B200 box)
+    assert balanced_pack_fraction(I_, L_, e, 0.0, 50e9) == 0.0
+    assert balanced_pack_fraction(0.0, 0.0, e, 1e9, 1e9) == 0.0
