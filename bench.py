@@ -734,7 +734,7 @@ def run_e2e(args, AF, par, wl, dev, world, total, sync_all):
         torch.cuda.current_stream(dev).synchronize()
 
     def run(K):
-        # public host-side entry, double buffered: while step k's batch is sliced, step k+1's batch crosses PCIe on a copy stream
+        # public host-side entry, pipelined (`depth` buffer sets): while step k is sliced, the next batches are packed on the host cores and cross PCIe on a copy stream
         # (groups of volumes; the groups that have arrived are expanded to the int64 + fp32 one-hot volumes of run_dl.py:261-264
         # together with the soft volume's min record on an expansion stream).  The upload of EVERY consumed batch - the first
         # one included - is issued inside this function, i.e. inside the timed region: K steps = K full uploads + K fwd/bwd.
